@@ -1,0 +1,99 @@
+// sta_host.cu — error plumbing, tensor-map construction, library-level C-ABI entry points.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "../../include/sta_b200.h"
+#include "sta_common.cuh"
+#include "sta_host.h"
+
+namespace sta {
+
+unsigned int* device_error_word() {
+  static unsigned int* word = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    if (cudaMalloc(&word, sizeof(unsigned int)) != cudaSuccess) { word = nullptr; return; }
+    cudaMemset(word, 0, sizeof(unsigned int));
+  });
+  return word;
+}
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(STA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return fail(STA_ERR_UNSUPPORTED, "tensor base %p is not 16-byte aligned", base);
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i];
+      if (strides_bytes[i] % 16 != 0)
+        return fail(STA_ERR_UNSUPPORTED, "stride[%d]=%llu bytes is not a multiple of 16", i,
+                    (unsigned long long)strides_bytes[i]);
+    }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(STA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return STA_OK;
+}
+
+}  // namespace sta
+
+extern "C" {
+
+int sta_version(void) { return STA_B200_VERSION; }
+
+const char* sta_last_error(void) { return sta::last_error_buf(); }
+
+int sta_device_error(unsigned int* code_out, int clear) {
+  unsigned int v = 0;
+  unsigned int* w = sta::device_error_word();
+  if (!w) return sta::fail(STA_ERR_CUDA, "could not allocate the device error word");
+  STA_CUDA_CHECK(cudaMemcpy(&v, w, sizeof(v), cudaMemcpyDeviceToHost));
+  if (code_out) *code_out = v;
+  if (clear && v != 0) {
+    STA_CUDA_CHECK(cudaMemset(w, 0, sizeof(v)));
+  }
+  if (v != 0) return sta::fail(STA_ERR_DEVICE, "device error word 0x%x (mbarrier wait timed out, id %u)", v, v & 0xff);
+  return STA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// sta_host.h — host-side helpers shared by the C-ABI translation units: error reporting and TMA tensor-map
+// construction.  No libcuda link dependency: cuTensorMapEncodeTiled is resolved through the runtime.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/sta_b200.h"  // return codes STA_OK / STA_ERR_*
+
+namespace sta {
+
+// thread-local last-error text ("message via sta_last_error() (thread-local)")
+char* last_error_buf();
+int fail(int code, const char* fmt, ...);
+
+
+#define STA_CUDA_CHECK(expr)                                                                 \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) return ::sta::fail(STA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+// one 4-byte device word per process that kernels bump on an mbarrier timeout (never freed)
+unsigned int* device_error_word();
+
+// Tiled fp16 tensor map with 128B swizzle.  dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+// box[0] must be <= 64 elements (128 bytes).  OOB elements are filled with zeros.
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+}  // namespace sta

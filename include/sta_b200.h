@@ -1,0 +1,169 @@
+/* sta_b200.h — C ABI of libsta_b200.so: the B200 (sm_100a) attention kernels behind the reference's
+ * `ldm.modules.attention` hook API.
+ *
+ * Reference interfaces replaced (paths under /root/reference/attention_optimization/stable-diffusion/):
+ *   sta_sattn_fwd / sta_sattn_bwd   CrossAttention.forward with context=None (self-attention `attn1`),
+ *                                   ldm/modules/attention.py:175-197 (einsum QK^T * scale -> softmax -> einsum PV)
+ *                                   and its autograd backward.
+ *   sta_xattn_fwd / sta_xattn_bwd   the (1 + n_obj) `attn2` calls plus the mask-gated alpha-blend of
+ *                                   BasicTransformerBlock._forward, ldm/modules/attention.py:278-294, evaluated
+ *                                   BEFORE `to_out` (the blend commutes with the affine `to_out`):
+ *                                     out[b]     = A_u[b]                                   b <  B  (uncond rows)
+ *                                     out[B + b] = A_g[b] + sum_i m_i[b,p] c_i[b] (A_i[b] - A_u[b])      (cond rows)
+ *                                   with A_x = softmax(q k_x^T * scale) v_x, and the backward d(out) ->
+ *                                   d(q), d(coef) (contexts are frozen, ldm/models/diffusion/ddpm.py:519-523).
+ *
+ * Rules of the boundary
+ *   - Plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise.
+ *   - The caller owns all buffers, including workspaces.  The library allocates nothing per call and creates
+ *     no streams: work is enqueued on `stream` (a cudaStream_t / CUstream passed as void*), no host sync inside.
+ *   - Return 0 on success, non-zero on error; text via sta_last_error() (thread-local).  Unsupported shapes are
+ *     errors, never a fallback.  No exceptions cross the boundary.
+ *   - fp16 storage, fp32 softmax/accumulation (what torch.autocast("cuda") gives the reference,
+ *     scripts/txt2img-gpt.py:310).
+ */
+#ifndef STA_B200_H_
+#define STA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STA_B200_VERSION 100 /* major*100 + minor */
+
+/* return codes */
+#define STA_OK 0
+#define STA_ERR_BAD_ARG 1
+#define STA_ERR_UNSUPPORTED 2
+#define STA_ERR_CUDA 3
+#define STA_ERR_DEVICE 4
+
+int sta_version(void);
+const char* sta_last_error(void);
+
+/* Reads (and optionally clears) the device-side error word that kernels set when a bounded mbarrier wait
+ * times out.  Synchronises the device (cudaMemcpy).  *code_out receives the raw word; returns STA_ERR_DEVICE if
+ * it was non-zero. */
+int sta_device_error(unsigned int* code_out, int clear);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Self-attention (attn1).  Tokens are laid out [batch, n, heads * head_dim] fp16 with arbitrary token/batch
+ * strides (in ELEMENTS) so q/k/v may be slices of one fused projection.  head_dim in {40, 80, 160} (SD-v1) or
+ * any multiple of 8 up to 160; strides and base pointers must keep every row 16-byte aligned.
+ * lse (optional, may be NULL): fp32 [batch, heads, n], natural-log-sum-exp of the scaled scores.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;  /* fp16 [batch, n, heads*head_dim], token stride o_token_stride */
+  float* lse; /* fp32 [batch, heads, n] or NULL */
+  int32_t batch, n, heads, head_dim;
+  int64_t q_token_stride, q_batch_stride;
+  int64_t k_token_stride, k_batch_stride;
+  int64_t v_token_stride, v_batch_stride;
+  int64_t o_token_stride, o_batch_stride;
+  float scale; /* head_dim ** -0.5 in the reference (attention.py:163) */
+} sta_sattn_fwd_args;
+
+int sta_sattn_fwd(const sta_sattn_fwd_args* args, void* stream);
+
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* out;   /* forward output, fp16 */
+  const void* d_out; /* fp16, same layout as out (do_token_stride / do_batch_stride) */
+  const float* lse;  /* from the forward */
+  void* d_q;         /* fp16 [batch, n, heads*head_dim] contiguous */
+  void* d_k;
+  void* d_v;
+  float* dq_accum; /* workspace, fp32 [batch, n, heads*head_dim]; zeroed by the library */
+  float* delta;    /* workspace, fp32 [batch, heads, n] */
+  int32_t batch, n, heads, head_dim;
+  int64_t q_token_stride, q_batch_stride;
+  int64_t k_token_stride, k_batch_stride;
+  int64_t v_token_stride, v_batch_stride;
+  int64_t o_token_stride, o_batch_stride;
+  int64_t do_token_stride, do_batch_stride;
+  float scale;
+} sta_sattn_bwd_args;
+
+int sta_sattn_bwd(const sta_sattn_bwd_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused dual cross-attention + mask-gated alpha-blend (attn2 x (1 + n_obj), attention.py:278-294).
+ *   q        fp16 [2*B, n, heads*head_dim]  rows [0,B) = unconditional half, [B,2B) = conditional half
+ *                                           (c_in = cat([uc, c]), ldm/models/diffusion/plms.py:306)
+ *   k_ctx    fp16 [B, 2 + n_obj, ctx_len, heads*head_dim]   to_k of: slot 0 = the prompt's unconditional
+ *   v_ctx    (same)                                          context, slot 1 = global prompt context,
+ *                                                            slot 2+i = local description i
+ *   mask     u8   [B, n_obj, n]     1 inside object i's disc (attention.py:254-261), else 0
+ *   coef     f32  [B, n_obj]        alpha_i for this timestep (plms.py:243, weighting_parameter[:, i])
+ *   out      fp16 [2*B, n, heads*head_dim]   pre-`to_out` blended attention output
+ *   lse      f32  [B, heads, 2 + n_obj, n]   optional (NULL for inference); slot order as k_ctx
+ * ctx_len <= 80 (77 for CLIP).  n_obj in [0, 8].
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q;
+  const void* k_ctx;
+  const void* v_ctx;
+  const uint8_t* mask;
+  const float* coef;
+  void* out;
+  float* lse;
+  int32_t prompts; /* B */
+  int32_t n, heads, head_dim, n_obj, ctx_len;
+  int64_t q_token_stride, q_batch_stride;
+  int64_t o_token_stride, o_batch_stride;
+  float scale;
+} sta_xattn_fwd_args;
+
+int sta_xattn_fwd(const sta_xattn_fwd_args* args, void* stream);
+
+typedef struct {
+  const void* q;
+  const void* k_ctx;
+  const void* v_ctx;
+  const uint8_t* mask;
+  const float* coef;
+  const float* lse;  /* from the forward */
+  const void* d_out; /* fp16 [2*B, n, heads*head_dim] */
+  void* d_q;         /* fp16 [2*B, n, heads*head_dim] contiguous */
+  float* d_coef;     /* fp32 [B, n_obj]; zeroed by the library, then accumulated atomically */
+  int32_t prompts;
+  int32_t n, heads, head_dim, n_obj, ctx_len;
+  int64_t q_token_stride, q_batch_stride;
+  int64_t do_token_stride, do_batch_stride;
+  float scale;
+} sta_xattn_bwd_args;
+
+int sta_xattn_bwd(const sta_xattn_bwd_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Test hook: one tcgen05 GEMM tile with caller-supplied UMMA descriptors (tests/test_probe_gpu.py pins the
+ * shared-memory/TMEM operand encodings the kernels above rely on).  Not part of the product path.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* a; /* fp16 row-major [a_tensor_rows, a_cols]; staged as TMA boxes of a_rows x 64 (OOB rows = 0) */
+  int32_t a_rows, a_tensor_rows, a_cols, a_in_tmem;
+  const void* b; /* fp16 row-major [b_tensor_rows, b_cols]; staged as TMA boxes of b_rows x 64 */
+  int32_t b_rows, b_tensor_rows, b_cols;
+  uint64_t a_desc_hi, b_desc_hi; /* descriptor templates with a zero start address */
+  int32_t nk;
+  uint32_t a_off[16], b_off[16]; /* per K-step byte offsets (TMEM column offsets when a_in_tmem) */
+  uint32_t idesc;
+  int32_t n;          /* accumulator columns to read back */
+  float* out;         /* fp32 [128, n] */
+  void* smem_dump;    /* optional: raw image of the staging shared memory */
+  int32_t dump_bytes;
+} sta_probe_args;
+
+int sta_probe_gemm(const sta_probe_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STA_B200_H_ */
