@@ -110,6 +110,8 @@ def load() -> C.CDLL:
         ("sta_xattn_fwd", XattnFwdArgs), ("sta_xattn_bwd", XattnBwdArgs),
         ("sta_probe_gemm", ProbeArgs),
     ):
+        if not hasattr(lib, name):  # reported by tests/test_cabi.py; calling it raises AttributeError
+            continue
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(argt), C.c_void_p]
         fn.restype = C.c_int
