@@ -97,6 +97,14 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
   }
 }
 
+// Whole-warp wait with a warp-uniform verdict: the .sync.aligned tcgen05 instructions that follow a wait must be
+// executed by all 32 lanes or by none, also on the (never expected) timeout path.
+__device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity, volatile int* dead, unsigned int* err,
+                                               unsigned int id) {
+  const bool ok = mbar_wait(bar, parity, dead, err, id);
+  return __all_sync(0xffffffffu, ok);
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -1,0 +1,331 @@
+// sta_sattn_fwd.cu — flash self-attention forward for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Replaces CrossAttention.forward with context=None (attn1), reference
+// ldm/modules/attention.py:175-197: sim = q k^T * scale; softmax(dim=-1); out = attn v — without ever
+// writing the [heads, N, N] score tensor to HBM.
+//
+// CTA = NQ query tiles of 128 rows of one (batch, head); 2 + 4*NQ warps:
+//   warp 0        TMA producer: Q tiles once, then K / V tiles of 128 keys through two mbarrier rings
+//   warp 1        MMA issuer (one lane): S_r = Q_r K_j^T  (SS, K-major operands)  and  O_r += P_r V_j
+//                 (TS: P_r is read from TMEM as packed fp16, V_j is an MN-major smem operand)
+//   warps 2..5    softmax of query tile 0: one thread per row, online softmax with lazy rescale
+//   warps 6..9    softmax of query tile 1 (NQ = 2)
+// TMEM columns: S_0 [0,128) S_1 [128,256) (P_r aliases the first 64 columns of S_r), O_r at 256 + r*DMMA.
+// The two query tiles ping-pong on the tensor pipe: while the softmax warps of tile 0 work on S_0 the
+// tensor core computes S_1 and O_1 += P_1 V, and vice versa.
+#include "../../include/sta_b200.h"
+#include "sta_common.cuh"
+#include "sta_host.h"
+
+namespace sta {
+
+constexpr int kBlockBytes = 128 * 128;  // one 64-column block of a 128-row tile
+
+template <int D>
+struct SattnCfg {
+  static constexpr int DMMA = (D + 15) / 16 * 16;   // K of the QK^T MMA and N of the PV MMA
+  static constexpr int NBLK = (D + 63) / 64;        // 64-column shared-memory blocks per tile
+  static constexpr int NQ = (DMMA <= 128) ? 2 : 1;  // query tiles per CTA (TMEM: 256 + NQ*DMMA <= 512)
+  static constexpr int KS = (NBLK == 1) ? 3 : 2;    // K ring depth
+  static constexpr int VS = (NBLK == 1) ? 3 : (NBLK == 2 ? 2 : 1);
+  static constexpr int TILE_BYTES = NBLK * kBlockBytes;
+  static constexpr int SMEM_BYTES = (NQ + KS + VS) * TILE_BYTES + 1024;
+  static constexpr int THREADS = 64 + 128 * NQ;
+  static constexpr int TMEM_O = 256;
+};
+
+struct SattnFwdParams {
+  __half* out;
+  float* lse;
+  int n, heads;
+  long long o_token_stride, o_batch_stride;
+  float scale_log2;  // scale * log2(e)
+  unsigned int* err;
+};
+
+template <int D>
+__global__ void __launch_bounds__(SattnCfg<D>::THREADS, 1)
+sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const SattnFwdParams p) {
+  using Cfg = SattnCfg<D>;
+  constexpr int NQ = Cfg::NQ, KS = Cfg::KS, VS = Cfg::VS, NBLK = Cfg::NBLK, DMMA = Cfg::DMMA;
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sK = sQ + NQ * Cfg::TILE_BYTES;
+  unsigned char* sV = sK + KS * Cfg::TILE_BYTES;
+
+  __shared__ uint64_t q_full, k_full[KS], k_empty[KS], v_full[VS], v_empty[VS];
+  __shared__ uint64_t s_full[NQ], p_ready[NQ], o_full[NQ];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int dead;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * (128 * NQ), h = blockIdx.y, b = blockIdx.z;
+  const int n = p.n;
+  const int T = (n + 127) / 128;                           // KV tiles
+  const int nq_active = (NQ == 2 && q0 + 128 < n) ? 2 : 1;  // second query tile may be past the end
+
+  if (tid == 0) {
+    dead = 0;
+    mbar_init(&q_full, 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < NQ; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_expect_tx(&q_full, nq_active * Cfg::TILE_BYTES);
+      for (int r = 0; r < nq_active; ++r)
+        for (int blk = 0; blk < NBLK; ++blk)
+          tma_load_4d(sQ + (r * NBLK + blk) * kBlockBytes, &tm_q, &q_full, blk * 64, h, q0 + r * 128, b);
+      for (int j = 0; j < T; ++j) {
+        const int ks = j % KS, vs = j % VS;
+        if (!mbar_wait(&k_empty[ks], ((j / KS) & 1) ^ 1, &dead, p.err, 10)) break;
+        mbar_expect_tx(&k_full[ks], Cfg::TILE_BYTES);
+        for (int blk = 0; blk < NBLK; ++blk)
+          tma_load_4d(sK + (ks * NBLK + blk) * kBlockBytes, &tm_k, &k_full[ks], blk * 64, h, j * 128, b);
+        if (!mbar_wait(&v_empty[vs], ((j / VS) & 1) ^ 1, &dead, p.err, 11)) break;
+        mbar_expect_tx(&v_full[vs], Cfg::TILE_BYTES);
+        for (int blk = 0; blk < NBLK; ++blk)
+          tma_load_4d(sV + (vs * NBLK + blk) * kBlockBytes, &tm_v, &v_full[vs], blk * 64, h, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);            // K-major operands
+      constexpr uint64_t vdesc_hi = umma_desc_hi_sw128(kBlockBytes, 1024);   // MN-major V: LBO = block stride
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, DMMA, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+
+      auto issue_qk = [&](int r, int ks) {
+#pragma unroll
+        for (int k = 0; k < DMMA / 16; ++k) {
+          const uint32_t off = (k / 4) * kBlockBytes + (k % 4) * 32;
+          umma_ss(tmem + r * 128, umma_desc(kdesc_hi, q_addr + r * Cfg::TILE_BYTES + off),
+                  umma_desc(kdesc_hi, k_addr + ks * Cfg::TILE_BYTES + off), idesc_qk, k > 0);
+        }
+        umma_commit(&s_full[r]);
+      };
+      auto issue_pv = [&](int r, int vs, bool acc) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tmem + Cfg::TMEM_O + r * DMMA, tmem + r * 128 + k * 8,
+                  umma_desc(vdesc_hi, v_addr + vs * Cfg::TILE_BYTES + k * 2048), idesc_pv, acc || k > 0);
+      };
+
+      bool ok = mbar_wait(&q_full, 0, &dead, p.err, 20) && mbar_wait(&k_full[0], 0, &dead, p.err, 21);
+      if (ok) {
+        tc_fence_after();
+        for (int r = 0; r < nq_active; ++r) issue_qk(r, 0);
+        umma_commit(&k_empty[0]);
+        for (int j = 0; j < T && ok; ++j) {
+          const int vs = j % VS, ks1 = (j + 1) % KS;
+          for (int r = 0; r < nq_active; ++r) {
+            ok = mbar_wait(&p_ready[r], j & 1, &dead, p.err, 22);
+            if (ok && r == 0) ok = mbar_wait(&v_full[vs], (j / VS) & 1, &dead, p.err, 23);
+            if (!ok) break;
+            tc_fence_after();
+            issue_pv(r, vs, j > 0);
+            if (r == nq_active - 1) umma_commit(&v_empty[vs]);
+            if (j + 1 < T) {
+              if (r == 0) {
+                ok = mbar_wait(&k_full[ks1], ((j + 1) / KS) & 1, &dead, p.err, 24);
+                if (!ok) break;
+                tc_fence_after();
+              }
+              issue_qk(r, ks1);
+              if (r == nq_active - 1) umma_commit(&k_empty[ks1]);
+            } else {
+              umma_commit(&o_full[r]);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== softmax / epilogue ================================
+    const int r = (warp - 2) >> 2;  // query tile of this warp
+    if (r < nq_active) {
+      const int row_in_tile = ((warp & 3) << 5) + lane;
+      const int row = q0 + r * 128 + row_in_tile;
+      const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+      const uint32_t s_addr = lane_addr + r * 128;
+      const uint32_t o_addr = lane_addr + Cfg::TMEM_O + r * DMMA;
+      float m_ref = -INFINITY, l = 0.f;
+      bool ok = true;
+      for (int j = 0; j < T; ++j) {
+        ok = mbar_wait_warp(&s_full[r], j & 1, &dead, p.err, 30);
+        if (!ok) break;
+        tc_fence_after();
+        uint32_t s[128];
+        tmem_ld32(s_addr, s);
+        tmem_ld32(s_addr + 32, s + 32);
+        tmem_ld32(s_addr + 64, s + 64);
+        tmem_ld32(s_addr + 96, s + 96);
+        tmem_ld_wait();
+        const int valid = n - j * 128;  // keys of this tile that exist
+        if (valid < 128) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= valid) s[c] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        if (j == 0) {
+          m_ref = mx;
+        } else {
+          // lazy rescale: keep the old reference unless the new maximum exceeds it by more than 2^8
+          const bool need = mx > m_ref + 8.f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float f = need ? fast_exp2(m_ref - mx) : 1.f;
+            if (need) m_ref = mx;
+            l *= f;
+#pragma unroll
+            for (int c0 = 0; c0 < DMMA; c0 += 16) {
+              uint32_t o[16];
+              tmem_ld16(o_addr + c0, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st16(o_addr + c0, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(s[c0 + 2 * i]), p.scale_log2, -m_ref));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(s[c0 + 2 * i + 1]), p.scale_log2, -m_ref));
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_half2(p0, p1);
+          }
+          tmem_st16(s_addr + (c0 >> 1), pk);
+        }
+        l += l0 + l1;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[r]);
+      }
+      // -------- epilogue: O / l -> fp16, natural-log LSE --------
+      ok = __all_sync(0xffffffffu, ok);
+      if (ok) ok = mbar_wait_warp(&o_full[r], 0, &dead, p.err, 31);
+      if (ok) {
+        tc_fence_after();
+        const float inv = 1.f / l;
+        __half* orow = p.out + (long long)b * p.o_batch_stride + (long long)row * p.o_token_stride + h * D;
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 8) {
+          uint32_t o[8];
+          tmem_ld8(o_addr + c0, o);
+          tmem_ld_wait();
+          if (row < n) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+            v.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+            v.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+            v.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c0) = v;
+          }
+        }
+        if (p.lse && row < n)
+          p.lse[((long long)b * p.heads + h) * n + row] = (m_ref + log2f(l)) * 0.6931471805599453f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int D>
+static int launch_sattn_fwd(const sta_sattn_fwd_args* a, cudaStream_t stream) {
+  using Cfg = SattnCfg<D>;
+  CUtensorMap tm_q, tm_k, tm_v;
+  const uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->heads, (uint64_t)a->n, (uint64_t)a->batch};
+  const uint32_t box[4] = {64, 1, 128, 1};
+  {
+    const uint64_t st[4] = {2, (uint64_t)D * 2, (uint64_t)a->q_token_stride * 2, (uint64_t)a->q_batch_stride * 2};
+    int rc = make_tmap_f16(&tm_q, a->q, 4, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t st[4] = {2, (uint64_t)D * 2, (uint64_t)a->k_token_stride * 2, (uint64_t)a->k_batch_stride * 2};
+    int rc = make_tmap_f16(&tm_k, a->k, 4, dims, st, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t st[4] = {2, (uint64_t)D * 2, (uint64_t)a->v_token_stride * 2, (uint64_t)a->v_batch_stride * 2};
+    int rc = make_tmap_f16(&tm_v, a->v, 4, dims, st, box);
+    if (rc) return rc;
+  }
+  SattnFwdParams p;
+  p.out = reinterpret_cast<__half*>(a->out);
+  p.lse = a->lse;
+  p.n = a->n;
+  p.heads = a->heads;
+  p.o_token_stride = a->o_token_stride;
+  p.o_batch_stride = a->o_batch_stride;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.err = device_error_word();
+  static bool attr_set = false;
+  if (!attr_set) {
+    STA_CUDA_CHECK(cudaFuncSetAttribute(sattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((a->n + 128 * Cfg::NQ - 1) / (128 * Cfg::NQ), a->heads, a->batch);
+  sattn_fwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_k, tm_v, p);
+  STA_CUDA_CHECK(cudaGetLastError());
+  return STA_OK;
+}
+
+}  // namespace sta
+
+extern "C" int sta_sattn_fwd(const sta_sattn_fwd_args* a, void* stream) {
+  using namespace sta;
+  if (!a || !a->q || !a->k || !a->v || !a->out) return fail(STA_ERR_BAD_ARG, "sta_sattn_fwd: null pointer");
+  if (a->batch < 1 || a->n < 1 || a->heads < 1) return fail(STA_ERR_BAD_ARG, "sta_sattn_fwd: empty shape");
+  if ((a->o_token_stride % 8) || (a->o_batch_stride % 8) || (reinterpret_cast<uintptr_t>(a->out) & 15))
+    return fail(STA_ERR_UNSUPPORTED, "sta_sattn_fwd: out rows must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (a->head_dim) {
+    case 40: return launch_sattn_fwd<40>(a, s);
+    case 80: return launch_sattn_fwd<80>(a, s);
+    case 160: return launch_sattn_fwd<160>(a, s);
+    default:
+      return fail(STA_ERR_UNSUPPORTED, "sta_sattn_fwd: head_dim %d not built (SD-v1 uses 40/80/160)", a->head_dim);
+  }
+}

@@ -1,0 +1,65 @@
+"""torch-facing wrappers of the C-ABI kernels (include/sta_b200.h) and their autograd Functions.
+
+PyTorch is plumbing here: it owns device memory and the stream; every attention FLOP runs in libsta_b200.so.
+There is no fallback path — a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import native
+
+# number of kernels launched by this module since import (bench.py reports it as `gpu_launches`)
+LAUNCHES = {"sattn_fwd": 0, "sattn_bwd": 0, "xattn_fwd": 0, "xattn_bwd": 0}
+
+
+def launch_count() -> int:
+    return sum(LAUNCHES.values())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require(t: torch.Tensor, name: str, dtype=torch.float16) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the sta_b200 kernels have no CPU fallback")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _token_major(t: torch.Tensor, name: str) -> Tuple[int, int]:
+    """(token_stride, batch_stride) in elements of a [b, n, c] tensor whose channel dim is dense."""
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise RuntimeError(f"{name} must be [batch, n, channels] with unit channel stride")
+    return t.stride(1), t.stride(0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# self-attention
+# ------------------------------------------------------------------------------------------------------
+def sattn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
+              need_lse: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """softmax(q k^T * scale) v per head.  q/k/v fp16 [b, n, heads*d] (may be strided views of one projection)."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _require(t, nm)
+    b, n, c = q.shape
+    d = c // heads
+    scale = float(d ** -0.5) if scale is None else float(scale)
+    out = torch.empty((b, n, c), device=q.device, dtype=torch.float16)
+    lse = torch.empty((b, heads, n), device=q.device, dtype=torch.float32) if need_lse else None
+    a = native.SattnFwdArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.lse = lse.data_ptr() if lse is not None else None
+    a.batch, a.n, a.heads, a.head_dim = b, n, heads, d
+    a.q_token_stride, a.q_batch_stride = _token_major(q, "q")
+    a.k_token_stride, a.k_batch_stride = _token_major(k, "k")
+    a.v_token_stride, a.v_batch_stride = _token_major(v, "v")
+    a.o_token_stride, a.o_batch_stride = _token_major(out, "out")
+    a.scale = scale
+    native.check(native.load().sta_sattn_fwd(C.byref(a), _stream()), "sta_sattn_fwd")
+    LAUNCHES["sattn_fwd"] += 1
+    return out, lse
