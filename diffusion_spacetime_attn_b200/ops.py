@@ -63,3 +63,46 @@ def sattn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     native.check(native.load().sta_sattn_fwd(C.byref(a), _stream()), "sta_sattn_fwd")
     LAUNCHES["sattn_fwd"] += 1
     return out, lse
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused dual cross-attention + alpha-blend
+# ------------------------------------------------------------------------------------------------------
+def xattn_fwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: Optional[torch.Tensor],
+              coef: Optional[torch.Tensor], heads: int, scale: Optional[float] = None,
+              need_lse: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """q fp16 [2B, n, C]; k_ctx/v_ctx fp16 [B, 2+n_obj, L, C] contiguous; mask u8 [B, n_obj, n]; coef f32 [B, n_obj].
+
+    Returns (out fp16 [2B, n, C], lse f32 [B, heads, 2+n_obj, n] | None).  See include/sta_b200.h.
+    """
+    _require(q, "q")
+    _require(k_ctx, "k_ctx")
+    _require(v_ctx, "v_ctx")
+    b2, n, c = q.shape
+    B = b2 // 2
+    if k_ctx.dim() != 4 or k_ctx.shape[0] != B or not k_ctx.is_contiguous() or not v_ctx.is_contiguous():
+        raise RuntimeError("k_ctx/v_ctx must be contiguous [B, 2+n_obj, ctx_len, C]")
+    n_obj, ctx_len = k_ctx.shape[1] - 2, k_ctx.shape[2]
+    d = c // heads
+    scale = float(d ** -0.5) if scale is None else float(scale)
+    if n_obj > 0:
+        _require(mask, "mask", torch.uint8)
+        _require(coef, "coef", torch.float32)
+        if tuple(mask.shape) != (B, n_obj, n) or not mask.is_contiguous():
+            raise RuntimeError(f"mask must be contiguous uint8 [{B}, {n_obj}, {n}], got {tuple(mask.shape)}")
+        if tuple(coef.shape) != (B, n_obj) or not coef.is_contiguous():
+            raise RuntimeError(f"coef must be contiguous float32 [{B}, {n_obj}], got {tuple(coef.shape)}")
+    out = torch.empty((b2, n, c), device=q.device, dtype=torch.float16)
+    lse = torch.zeros((B, heads, 2 + n_obj, n), device=q.device, dtype=torch.float32) if need_lse else None
+    a = native.XattnFwdArgs()
+    a.q, a.k_ctx, a.v_ctx, a.out = q.data_ptr(), k_ctx.data_ptr(), v_ctx.data_ptr(), out.data_ptr()
+    a.mask = mask.data_ptr() if n_obj > 0 else None
+    a.coef = coef.data_ptr() if n_obj > 0 else None
+    a.lse = lse.data_ptr() if lse is not None else None
+    a.prompts, a.n, a.heads, a.head_dim, a.n_obj, a.ctx_len = B, n, heads, d, n_obj, ctx_len
+    a.q_token_stride, a.q_batch_stride = _token_major(q, "q")
+    a.o_token_stride, a.o_batch_stride = _token_major(out, "out")
+    a.scale = scale
+    native.check(native.load().sta_xattn_fwd(C.byref(a), _stream()), "sta_xattn_fwd")
+    LAUNCHES["xattn_fwd"] += 1
+    return out, lse
