@@ -106,3 +106,32 @@ def xattn_fwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: O
     native.check(native.load().sta_xattn_fwd(C.byref(a), _stream()), "sta_xattn_fwd")
     LAUNCHES["xattn_fwd"] += 1
     return out, lse
+
+
+def xattn_bwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: Optional[torch.Tensor],
+              coef: Optional[torch.Tensor], lse: torch.Tensor, d_out: torch.Tensor, heads: int,
+              scale: Optional[float] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Backward of xattn_fwd: returns (d_q fp16 [2B, n, C], d_coef f32 [B, n_obj] | None)."""
+    _require(q, "q")
+    _require(d_out, "d_out")
+    _require(lse, "lse", torch.float32)
+    b2, n, c = q.shape
+    B = b2 // 2
+    n_obj, ctx_len = k_ctx.shape[1] - 2, k_ctx.shape[2]
+    d = c // heads
+    scale = float(d ** -0.5) if scale is None else float(scale)
+    d_q = torch.empty((b2, n, c), device=q.device, dtype=torch.float16)
+    d_coef = torch.empty((B, n_obj), device=q.device, dtype=torch.float32) if n_obj > 0 else None
+    a = native.XattnBwdArgs()
+    a.q, a.k_ctx, a.v_ctx = q.data_ptr(), k_ctx.data_ptr(), v_ctx.data_ptr()
+    a.mask = mask.data_ptr() if n_obj > 0 else None
+    a.coef = coef.data_ptr() if n_obj > 0 else None
+    a.lse, a.d_out, a.d_q = lse.data_ptr(), d_out.data_ptr(), d_q.data_ptr()
+    a.d_coef = d_coef.data_ptr() if d_coef is not None else None
+    a.prompts, a.n, a.heads, a.head_dim, a.n_obj, a.ctx_len = B, n, heads, d, n_obj, ctx_len
+    a.q_token_stride, a.q_batch_stride = _token_major(q, "q")
+    a.do_token_stride, a.do_batch_stride = _token_major(d_out, "d_out")
+    a.scale = scale
+    native.check(native.load().sta_xattn_bwd(C.byref(a), _stream()), "sta_xattn_bwd")
+    LAUNCHES["xattn_bwd"] += 1
+    return d_q, d_coef

@@ -99,3 +99,42 @@ def test_xattn_linearity_in_coef():
     f0, f1, f2 = f(torch.zeros_like(coef)), f(coef), f(2 * coef)
     torch.cuda.synchronize()
     assert ((f2 - f1) - (f1 - f0)).abs().max().item() < 2e-2
+
+
+BWD_SHAPES = [
+    (1, 4096, 8, 40, 2),
+    (1, 1024, 8, 80, 2),
+    (1, 256, 8, 160, 2),
+    (1, 64, 8, 160, 3),
+    (1, 1024, 8, 80, 0),
+    (2, 576, 8, 160, 6),
+    (2, 2304, 4, 80, 5),
+    (1, 100, 2, 40, 1),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", BWD_SHAPES, ids=[str(s) for s in BWD_SHAPES])
+def test_xattn_bwd_matches_oracle_autograd(shape):
+    """d(q) and d(coef) against torch autograd through the oracle restatement (fp32, same fp16-rounded inputs).
+
+    Tolerances: d_q element-wise 3e-3 + 2e-2*|ref| (fp16 dS operand); d_coef relative 2e-2.
+    """
+    B, n, h, d, n_obj = shape
+    q, k, v, masks, coef = make_case(*shape, seed=7)
+    g = torch.Generator().manual_seed(11)
+    d_out = (torch.randn(2 * B, n, h * d, generator=g) * 0.1).half()
+    qf = q.float().requires_grad_(True)
+    cf = coef.clone().requires_grad_(n_obj > 0)
+    ref = O.dual_cross_attention_core(qf, k.float(), v.float(), masks, cf, h)
+    (ref * d_out.float()).sum().backward()
+    dev = lambda t: t.cuda()
+    out, lse = ops.xattn_fwd(dev(q), dev(k), dev(v), dev(masks) if n_obj else None, dev(coef) if n_obj else None, h)
+    d_q, d_coef = ops.xattn_bwd(dev(q), dev(k), dev(v), dev(masks) if n_obj else None,
+                                dev(coef) if n_obj else None, lse, dev(d_out), h)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    _close(d_q, qf.grad, atol=3e-3, rtol=2e-2)
+    if n_obj:
+        rel = (d_coef.cpu() - cf.grad).abs() / (cf.grad.abs() + 1e-2 * cf.grad.abs().max() + 1e-6)
+        assert rel.max().item() < 2e-2, f"d_coef rel err {rel.max().item():.3e}: {d_coef.cpu()} vs {cf.grad}"
