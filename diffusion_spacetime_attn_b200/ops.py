@@ -135,3 +135,86 @@ def xattn_bwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: O
     native.check(native.load().sta_xattn_bwd(C.byref(a), _stream()), "sta_xattn_bwd")
     LAUNCHES["xattn_bwd"] += 1
     return d_q, d_coef
+
+
+def sattn_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, lse: torch.Tensor,
+              d_out: torch.Tensor, heads: int, scale: Optional[float] = None):
+    """Backward of sattn_fwd: returns (d_q, d_k, d_v) fp16 [b, n, C]."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (d_out, "d_out")):
+        _require(t, nm)
+    _require(lse, "lse", torch.float32)
+    b, n, c = q.shape
+    d = c // heads
+    scale = float(d ** -0.5) if scale is None else float(scale)
+    d_qkv = torch.empty((3, b, n, c), device=q.device, dtype=torch.float16)
+    dq_accum = torch.empty((b, n, c), device=q.device, dtype=torch.float32)
+    delta = torch.empty((b, heads, n), device=q.device, dtype=torch.float32)
+    a = native.SattnBwdArgs()
+    a.q, a.k, a.v, a.out, a.d_out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), d_out.data_ptr()
+    a.lse = lse.data_ptr()
+    a.d_q, a.d_k, a.d_v = d_qkv[0].data_ptr(), d_qkv[1].data_ptr(), d_qkv[2].data_ptr()
+    a.dq_accum, a.delta = dq_accum.data_ptr(), delta.data_ptr()
+    a.batch, a.n, a.heads, a.head_dim = b, n, heads, d
+    a.q_token_stride, a.q_batch_stride = _token_major(q, "q")
+    a.k_token_stride, a.k_batch_stride = _token_major(k, "k")
+    a.v_token_stride, a.v_batch_stride = _token_major(v, "v")
+    a.o_token_stride, a.o_batch_stride = _token_major(out, "out")
+    a.do_token_stride, a.do_batch_stride = _token_major(d_out, "d_out")
+    a.scale = scale
+    native.check(native.load().sta_sattn_bwd(C.byref(a), _stream()), "sta_sattn_bwd")
+    LAUNCHES["sattn_bwd"] += 3  # delta, main, dq cast
+    return d_qkv[0], d_qkv[1], d_qkv[2]
+
+
+# ------------------------------------------------------------------------------------------------------
+# autograd
+# ------------------------------------------------------------------------------------------------------
+class SelfAttentionFn(torch.autograd.Function):
+    """attn1 core.  Saves q, k, v, out, lse (flash style) — the [heads, N, N] matrix is never stored."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads):
+        need = any(ctx.needs_input_grad[:3])
+        out, lse = sattn_fwd(q, k, v, heads, need_lse=need)
+        if need:
+            ctx.save_for_backward(q, k, v, out, lse)
+            ctx.heads = heads
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v, out, lse = ctx.saved_tensors
+        if d_out.stride(2) != 1:
+            d_out = d_out.contiguous()
+        d_q, d_k, d_v = sattn_bwd(q, k, v, out, lse, d_out.to(torch.float16), ctx.heads)
+        return d_q, d_k, d_v, None
+
+
+class DualCrossAttentionFn(torch.autograd.Function):
+    """Fused (1 + n_obj) x attn2 + alpha-blend, before `to_out`.  Gradients flow to q and coef only: the
+    context K/V are projections of frozen text embeddings (reference ddpm.py:519-523)."""
+
+    @staticmethod
+    def forward(ctx, q, k_ctx, v_ctx, mask, coef, heads):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[4]
+        out, lse = xattn_fwd(q, k_ctx, v_ctx, mask, coef, heads, need_lse=need)
+        if need:
+            ctx.save_for_backward(q, k_ctx, v_ctx, mask, coef, lse)
+            ctx.heads = heads
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k_ctx, v_ctx, mask, coef, lse = ctx.saved_tensors
+        if d_out.stride(2) != 1:
+            d_out = d_out.contiguous()
+        d_q, d_coef = xattn_bwd(q, k_ctx, v_ctx, mask, coef, lse, d_out.to(torch.float16), ctx.heads)
+        return d_q, None, None, None, d_coef, None
+
+
+def self_attention(q, k, v, heads):
+    return SelfAttentionFn.apply(q, k, v, heads)
+
+
+def dual_cross_attention(q, k_ctx, v_ctx, mask, coef, heads):
+    return DualCrossAttentionFn.apply(q, k_ctx, v_ctx, mask, coef, heads)

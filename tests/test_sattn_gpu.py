@@ -87,3 +87,51 @@ def test_sattn_rejects_unsupported_head_dim_and_cpu_tensors():
         ops.sattn_fwd(q, q, q, heads=1)  # d = 64 is not built: an error, never a fallback
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.sattn_fwd(q.cpu(), q.cpu(), q.cpu(), heads=1)
+
+
+BWD_SHAPES = [
+    (2, 64, 8, 160),
+    (2, 256, 8, 160),
+    (2, 1024, 8, 80),
+    (1, 4096, 8, 40),
+    (1, 576, 4, 160),
+    (1, 300, 2, 40),
+    (1, 129, 1, 80),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", BWD_SHAPES, ids=[str(s) for s in BWD_SHAPES])
+def test_sattn_bwd_matches_oracle_autograd(shape):
+    """dQ, dK, dV against torch autograd through the oracle (fp32, same fp16-rounded inputs).
+    Tolerance 3e-3 * max|ref| + 2e-2 * |ref| element-wise (P and dS are fp16 MMA operands)."""
+    b, n, h, d = shape
+    q, k, v = _inputs(b, n, h, d, seed=9)
+    g = torch.Generator().manual_seed(10)
+    d_out = (torch.randn(b, n, h * d, generator=g) * 0.1).half()
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = O.attention_core(qf, kf, vf, h)
+    (ref * d_out.float()).sum().backward()
+    dq, dk, dv = q.cuda(), k.cuda(), v.cuda()
+    out, lse = ops.sattn_fwd(dq, dk, dv, h)
+    g_q, g_k, g_v = ops.sattn_bwd(dq, dk, dv, out, lse, d_out.cuda(), h)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    for got, want, nm in ((g_q, qf.grad, "dq"), (g_k, kf.grad, "dk"), (g_v, vf.grad, "dv")):
+        err = (got.float().cpu() - want).abs()
+        bound = 3e-3 * want.abs().max() + 2e-2 * want.abs()
+        bad = (err > bound).sum().item()
+        assert bad == 0, f"{nm}: {bad} elements out of tolerance, max err {err.max().item():.3e} (ref max {want.abs().max().item():.3e})"
+
+
+@pytest.mark.gpu
+def test_autograd_functions_route_through_kernels():
+    b, n, h, d = 2, 256, 8, 40
+    q, k, v = (t.cuda().requires_grad_(True) for t in _inputs(b, n, h, d, seed=12))
+    before = dict(ops.LAUNCHES)
+    out = ops.self_attention(q, k, v, h)
+    out.float().square().sum().backward()
+    torch.cuda.synchronize()
+    assert ops.LAUNCHES["sattn_fwd"] == before["sattn_fwd"] + 1
+    assert ops.LAUNCHES["sattn_bwd"] == before["sattn_bwd"] + 3
+    assert q.grad is not None and torch.isfinite(q.grad.float()).all()
