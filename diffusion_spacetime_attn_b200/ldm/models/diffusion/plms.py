@@ -1,0 +1,229 @@
+"""PLMS sampler WITH the alpha (blend-weight) optimisation, keeping the reference's public API
+(/root/reference/.../ldm/models/diffusion/plms.py: PLMSSampler.sample :114-180, plms_sampling :182-293,
+p_sample_plms :296-358, DCLIPLoss :21-61).
+
+Behaviour kept: 3 "epochs", each a full differentiable S-step trajectory from the same x_T (S + 1 UNet evaluations:
+the first step evaluates the model twice with the same coefficient column, :341-345), VAE decode, CLIP loss
+(global + 5 x per-object crops, :252-273), backward to `weighting_parameter`, one Adam(lr=0.005) step; the image of
+the LAST epoch is written to result_outputs/final{epoch}_s{seed}_index_{idx}.png (:280-288).
+
+Generalised (the reference hard-codes them): the number of columns of `weighting_parameter` is S (not
+50); the "first step" the attention blocks key on is the schedule's largest timestep (not 981); B > 1 prompts per call
+(rows [uc x B, c x B]); the crop size follows the decoded image (not 512).  Host-side differences that do not change
+the arithmetic: per-step scalars are Python floats (no per-step device tensors), the timestep reaches the attention
+blocks as a host int (no sync), local embeddings are handed over in memory (`local_conditionings=`) instead of
+through c{i}_*.pt files.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ...modules.diffusionmodules.util import make_ddim_sampling_parameters, make_ddim_timesteps
+
+mode = "fix_radius_0p2"
+
+
+def _per_prompt(value, B):
+    """bboxs / names may be given once (shared by all prompts) or per prompt."""
+    if value is None:
+        return [[] for _ in range(B)]
+    if len(value) and isinstance(value[0], (list, tuple)) and len(value[0]) and isinstance(value[0][0], (list, tuple)):
+        return [list(v) for v in value]
+    if len(value) and isinstance(value[0], (list, tuple)) and (len(value[0]) == 0 or isinstance(value[0][0], str)):
+        return [list(v) for v in value]
+    return [list(value) for _ in range(B)]
+
+
+class PLMSSampler(object):
+    method = "plms"
+
+    def __init__(self, model, schedule="linear", clip_loss_model=None, num_epochs=3, lr=0.005,
+                 weight_initialize_coef=5.0, local_loss_weight=5.0, save_images=True, out_dir="result_outputs",
+                 verbose=False, **kwargs):
+        super().__init__()
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+        if clip_loss_model is None:
+            from ...modules.encoders.clip_loss import DCLIPLoss
+
+            clip_loss_model = DCLIPLoss(device=model.device)
+        self.clip_loss_model = clip_loss_model
+        self.clip_loss_model.requires_grad_(False)
+        self.num_epochs, self.lr = num_epochs, lr
+        self.weight_initialize_coef, self.local_loss_weight = weight_initialize_coef, local_loss_weight
+        self.save_images, self.out_dir, self.verbose = save_images, out_dir, verbose
+        self.last_result = None
+
+    # ------------------------------------------------------------------------------------------------
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0.0, verbose=True):
+        if ddim_eta != 0:
+            raise ValueError("ddim_eta must be 0 for PLMS")
+        self.ddim_timesteps = make_ddim_timesteps(ddim_discretize, ddim_num_steps, self.ddpm_num_timesteps, verbose=False)
+        acp = self.model.alphas_cumprod.detach().float().cpu().numpy()
+        sigmas, alphas, alphas_prev = make_ddim_sampling_parameters(acp, self.ddim_timesteps, ddim_eta, verbose=False)
+        self.ddim_sigmas, self.ddim_alphas, self.ddim_alphas_prev = sigmas, alphas, alphas_prev
+        self.ddim_sqrt_one_minus_alphas = np.sqrt(1.0 - alphas)
+        dev = self.model.device
+        self._ts = {int(t): torch.full((1,), int(t), device=dev, dtype=torch.long) for t in self.ddim_timesteps}
+
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0.0, mask=None, x0=None, temperature=1.0, noise_dropout=0.0,
+               score_corrector=None, corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100,
+               unconditional_guidance_scale=1.0, unconditional_conditioning=None, text_index=None, curr_text="",
+               bboxs_curr=None, seed=None, prompt_idx=None, object_names=None, local_conditionings=None,
+               optimize_alpha=True, alpha=None, **kwargs):
+        if conditioning is not None and conditioning.shape[0] != batch_size:
+            print(f"Warning: Got {conditioning.shape[0]} conditionings but batch-size is {batch_size}")
+        if mask is not None or x0 is not None or score_corrector is not None or quantize_x0:
+            raise NotImplementedError("inpainting masks / score correctors are not on the txt2img-* path")
+        self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=False)
+        C, H, W = shape
+        self.plms_sampling(conditioning, (batch_size, C, H, W), x_T=x_T,
+                           unconditional_guidance_scale=unconditional_guidance_scale,
+                           unconditional_conditioning=unconditional_conditioning, text_index=text_index,
+                           curr_text=curr_text, bboxs_curr=bboxs_curr, seed=seed, prompt_idx=prompt_idx,
+                           object_names=object_names, local_conditionings=local_conditionings,
+                           optimize_alpha=optimize_alpha, alpha=alpha)
+        return None
+
+    # ------------------------------------------------------------------------------------------------
+    def _trajectory(self, img, cond, uc, scale, W, bboxes, text_index):
+        time_range = np.flip(self.ddim_timesteps)
+        total = len(time_range)
+        old_eps: List[torch.Tensor] = []
+        for i, step in enumerate(time_range):
+            index = total - i - 1
+            t_next = int(time_range[min(i + 1, total - 1)])
+            coef = W[:, :, i] if W is not None else None
+            img, _, e_t = self.p_sample_plms(img, cond, int(step), index=index, unconditional_guidance_scale=scale,
+                                             unconditional_conditioning=uc, old_eps=old_eps, t_next=t_next,
+                                             text_index=text_index, coef=coef, bboxs_curr=bboxes)
+            old_eps.append(e_t)
+            if len(old_eps) >= 4:
+                old_eps.pop(0)
+        return img
+
+    def _loss(self, images, texts, bboxes_pp, names_pp):
+        """plms.py:252-273 per prompt; images [B, 3, Hpx, Wpx] in [0, 1]."""
+        total = images.new_zeros((), dtype=torch.float32)
+        per_prompt = []
+        for b in range(images.shape[0]):
+            img = images[b].float()
+            size_y, size_x = img.shape[1], img.shape[2]
+            loss = self.clip_loss_model.forward_2(img, texts[b]).sum()
+            for box, name in zip(bboxes_pp[b], names_pp[b]):
+                x1, x2 = max(box[0] - 0.2, 0), min(box[0] + 0.2, 1)
+                y1, y2 = max(box[1] - 0.2, 0), min(box[1] + 0.2, 1)
+                obj = name.lower().replace("the ", "")
+                crop = img[:, int(size_y * y1):int(size_y * y2), int(size_x * x1):int(size_x * x2)]
+                loss = loss + self.local_loss_weight * self.clip_loss_model.forward_3(crop, "A photo of " + obj).sum()
+            per_prompt.append(loss)
+            total = total + loss
+        return total, per_prompt
+
+    def plms_sampling(self, cond, shape, x_T=None, unconditional_guidance_scale=1.0, unconditional_conditioning=None,
+                      text_index=None, curr_text="", bboxs_curr=None, seed=None, prompt_idx=None, object_names=None,
+                      local_conditionings=None, optimize_alpha=True, alpha=None):
+        assert seed is not None
+        device = self.model.device
+        B = shape[0]
+        bboxes_pp = _per_prompt(bboxs_curr, B)
+        names_pp = _per_prompt(object_names, B)
+        n_obj = len(bboxes_pp[0])
+        assert all(len(bb) == n_obj for bb in bboxes_pp), "prompts of one batch must have the same number of objects"
+        assert all(len(nm) == len(bb) for nm, bb in zip(names_pp, bboxes_pp))
+        texts = [curr_text] * B if isinstance(curr_text, str) else list(curr_text)
+        idxs = [prompt_idx] * B if not isinstance(prompt_idx, (list, tuple)) else list(prompt_idx)
+        img_input = torch.randn(shape, device=device) if x_T is None else x_T
+        S = len(self.ddim_timesteps)
+
+        unet = self.model.model.diffusion_model
+        unet.set_local_contexts(local_conditionings, first_timestep=int(self.ddim_timesteps[-1]))
+        bboxes_arg = bboxes_pp if B > 1 else bboxes_pp[0]
+
+        if n_obj:
+            W = torch.full((B, n_obj, S), self.weight_initialize_coef / n_obj, device=device, dtype=torch.float32)
+            if alpha is not None:
+                W = torch.as_tensor(alpha, device=device, dtype=torch.float32).reshape(-1, n_obj, S).expand(B, n_obj, S).clone()
+        else:
+            W = torch.zeros((B, 0, S), device=device, dtype=torch.float32)
+        do_opt = bool(optimize_alpha and n_obj > 0)
+        optimizer = None
+        if do_opt:
+            W.requires_grad_(True)
+            optimizer = torch.optim.Adam([W], lr=self.lr)
+        epochs = self.num_epochs if do_opt else 1
+        losses, img, decoded = [], None, None
+        for epoch in range(epochs):
+            with torch.set_grad_enabled(do_opt):
+                img = self._trajectory(img_input.clone(), cond, unconditional_conditioning,
+                                       unconditional_guidance_scale, W if n_obj else None, bboxes_arg, text_index)
+                if do_opt or self.save_images:
+                    decoded = self.model.decode_first_stage(img)
+                    decoded = torch.clamp((decoded + 1.0) / 2.0, min=0.0, max=1.0)
+                if do_opt:
+                    loss, per_prompt = self._loss(decoded, texts, bboxes_pp, names_pp)
+                    optimizer.zero_grad(set_to_none=True)
+                    loss.backward()
+                    optimizer.step()
+                    losses.append([float(v) for v in torch.stack(per_prompt).detach().cpu()])
+            if epoch == epochs - 1 and self.save_images and decoded is not None:
+                self._save(decoded.detach(), epoch if do_opt else 2, seed, idxs)
+        unet.set_local_contexts(None)
+        self.last_result = {"latent": img.detach(), "weighting_parameter": W.detach(), "losses": losses,
+                            "image": decoded.detach() if decoded is not None else None}
+        return None
+
+    def _save(self, images, epoch, seed, idxs):
+        from PIL import Image
+
+        os.makedirs(self.out_dir, exist_ok=True)
+        arr = (255.0 * images.float().cpu().numpy()).transpose(0, 2, 3, 1).astype(np.uint8)
+        for b, idx in enumerate(idxs):
+            Image.fromarray(arr[b]).save(os.path.join(self.out_dir, "final%d_s%d_index_%d.png" % (epoch, seed, idx or 0)))
+
+    # ------------------------------------------------------------------------------------------------
+    def _model_output(self, x, t_int, c, uc, scale, text_index, coef, bboxs_curr):
+        """get_model_output (plms.py:299-308): rows [uncond x B, cond x B] through apply_model_extra, then CFG."""
+        B = x.shape[0]
+        t_in = self._ts[t_int].expand(2 * B)
+        x_in = torch.cat([x, x])
+        c_in = torch.cat([uc, c])
+        e_t_uncond, e_t = self.model.apply_model_extra(x_in, text_index, t_in, c_in, coef=coef, bboxs_curr=bboxs_curr,
+                                                       step_time=t_int).chunk(2)
+        return e_t_uncond + scale * (e_t - e_t_uncond)
+
+    def _x_prev_and_pred_x0(self, x, e_t, index):
+        a_t, a_prev = float(self.ddim_alphas[index]), float(self.ddim_alphas_prev[index])
+        sigma_t, sqrt_1m = float(self.ddim_sigmas[index]), float(self.ddim_sqrt_one_minus_alphas[index])
+        pred_x0 = (x - sqrt_1m * e_t) / (a_t ** 0.5)
+        dir_xt = ((1.0 - a_prev - sigma_t ** 2) ** 0.5) * e_t
+        return (a_prev ** 0.5) * pred_x0 + dir_xt, pred_x0  # eta = 0: no noise term
+
+    def p_sample_plms(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
+                      temperature=1.0, noise_dropout=0.0, score_corrector=None, corrector_kwargs=None,
+                      unconditional_guidance_scale=1.0, unconditional_conditioning=None, old_eps=None, t_next=None,
+                      text_index=None, coef=None, bboxs_curr=None):
+        t_int = int(t if not torch.is_tensor(t) else t.flatten()[0].item())
+        tn_int = int(t_next if not torch.is_tensor(t_next) else t_next.flatten()[0].item())
+        out = lambda xx, tt: self._model_output(xx, tt, c, unconditional_conditioning, unconditional_guidance_scale,
+                                                text_index, coef, bboxs_curr)
+        e_t = out(x, t_int)
+        if self.method == "ddim":
+            e_t_prime = e_t
+        elif len(old_eps) == 0:  # pseudo improved Euler: second evaluation with the SAME coefficient column
+            x_prev, _ = self._x_prev_and_pred_x0(x, e_t, index)
+            e_t_prime = (e_t + out(x_prev, tn_int)) / 2
+        elif len(old_eps) == 1:
+            e_t_prime = (3 * e_t - old_eps[-1]) / 2
+        elif len(old_eps) == 2:
+            e_t_prime = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+        else:
+            e_t_prime = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        x_prev, pred_x0 = self._x_prev_and_pred_x0(x, e_t_prime, index)
+        return x_prev, pred_x0, e_t

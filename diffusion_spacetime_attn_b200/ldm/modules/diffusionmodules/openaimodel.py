@@ -1,0 +1,215 @@
+"""SD-v1 UNet with the reference's module tree and forward signature
+(/root/reference/.../ldm/modules/diffusionmodules/openaimodel.py: TimestepEmbedSequential :74-88, ResBlock
+:163-275, UNetModel :413-742), so `model.diffusion_model.*` checkpoint keys load unchanged.
+
+Only what `configs/stable-diffusion/v1-inference.yaml:29-44` instantiates is built (spatial transformers at every
+attention resolution, conv resampling, no class conditioning, no scale-shift norm).  The convolutions, GroupNorms
+and the feed-forward stay library calls (cuDNN / cuBLAS through torch); the attention inside every
+SpatialTransformer runs on the sm_100a kernels (ldm/modules/attention.py of this package).
+
+Additions over the reference API (all optional, the reference call shape keeps working):
+  * `timesteps[0]` is forwarded to the blocks as a Python int when the caller passes `step_time=` (no device sync);
+  * `set_local_contexts()` / `reset_attention_cache()` hand the per-object embeddings to all 16 blocks in memory.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch as th
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..attention import BasicTransformerBlock, SpatialTransformer
+from .util import checkpoint, conv_nd, linear, normalization, timestep_embedding, zero_module
+
+
+class TimestepBlock(nn.Module):
+    """Marker: forward(x, emb)."""
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    def forward(self, x, emb, context=None, time=None, text_index=None, coef=None, bboxs_curr=None):
+        for layer in self:
+            if isinstance(layer, TimestepBlock):
+                x = layer(x, emb)
+            elif isinstance(layer, SpatialTransformer):
+                x = layer(x, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
+            else:
+                x = layer(x)
+        return x
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        if use_conv:
+            self.conv = conv_nd(dims, self.channels, self.out_channels, 3, padding=padding)
+
+    def forward(self, x):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        return self.conv(x) if self.use_conv else x
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        if use_conv:
+            self.op = conv_nd(dims, self.channels, self.out_channels, 3, stride=2, padding=padding)
+        else:
+            self.op = nn.AvgPool2d(kernel_size=2, stride=2)
+
+    def forward(self, x):
+        return self.op(x)
+
+
+class ResBlock(TimestepBlock):
+    """GroupNorm-SiLU-conv, + timestep embedding, GroupNorm-SiLU-conv, skip (reference :252-275)."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, dims=2, use_checkpoint=False):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_checkpoint = use_checkpoint
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(),
+                                       conv_nd(dims, channels, self.out_channels, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(
+            normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+            zero_module(conv_nd(dims, self.out_channels, self.out_channels, 3, padding=1)),
+        )
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = conv_nd(dims, channels, self.out_channels, 1)
+
+    def forward(self, x, emb):
+        flag = self.use_checkpoint and x.shape[-1] * x.shape[-2] >= getattr(self, "checkpoint_min_tokens", 0)
+        return checkpoint(self._forward, (x, emb), self.parameters(), flag)
+
+    def _forward(self, x, emb):
+        h = self.in_layers(x)
+        emb_out = self.emb_layers(emb).type(h.dtype)
+        h = h + emb_out[:, :, None, None]
+        h = self.out_layers(h)
+        return self.skip_connection(x) + h
+
+
+class UNetModel(nn.Module):
+    def __init__(self, image_size=32, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2,
+                 attention_resolutions=(4, 2, 1), dropout=0, channel_mult=(1, 2, 4, 4), conv_resample=True, dims=2,
+                 num_classes=None, use_checkpoint=False, use_fp16=False, num_heads=8, num_head_channels=-1,
+                 num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
+                 use_new_attention_order=False, use_spatial_transformer=True, transformer_depth=1, context_dim=768,
+                 n_embed=None, legacy=False):
+        super().__init__()
+        if not use_spatial_transformer or context_dim is None:
+            raise ValueError("only the spatial-transformer UNet of SD-v1 is built")
+        if num_classes is not None or use_scale_shift_norm or resblock_updown or n_embed is not None:
+            raise ValueError("class conditioning / scale-shift norm / resblock resampling are not used by SD-v1")
+        if isinstance(context_dim, (list, tuple)) or type(context_dim).__name__ == "ListConfig":
+            context_dim = list(context_dim)[0]
+        self.in_channels, self.model_channels, self.out_channels = in_channels, model_channels, out_channels
+        self.num_res_blocks, self.attention_resolutions = num_res_blocks, tuple(attention_resolutions)
+        self.channel_mult, self.num_heads = tuple(channel_mult), num_heads
+        self.num_classes = None
+        self.dtype = th.float32
+
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(linear(model_channels, time_embed_dim), nn.SiLU(),
+                                        linear(time_embed_dim, time_embed_dim))
+
+        def res(cin, cout):
+            return ResBlock(cin, time_embed_dim, dropout, out_channels=cout, dims=dims, use_checkpoint=use_checkpoint)
+
+        def attn(ch):
+            heads = num_heads if num_head_channels == -1 else ch // num_head_channels
+            return SpatialTransformer(ch, heads, ch // heads, depth=transformer_depth, context_dim=context_dim)
+
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(conv_nd(dims, in_channels, model_channels, 3, padding=1))])
+        skip_chans = [model_channels]
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(self.channel_mult):
+            for _ in range(num_res_blocks):
+                layers: List[nn.Module] = [res(ch, mult * model_channels)]
+                ch = mult * model_channels
+                if ds in self.attention_resolutions:
+                    layers.append(attn(ch))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                skip_chans.append(ch)
+            if level != len(self.channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims, out_channels=ch)))
+                skip_chans.append(ch)
+                ds *= 2
+
+        self.middle_block = TimestepEmbedSequential(res(ch, ch), attn(ch), res(ch, ch))
+
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(self.channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [res(ch + skip_chans.pop(), model_channels * mult)]
+                ch = model_channels * mult
+                if ds in self.attention_resolutions:
+                    layers.append(attn(ch))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, dims=dims, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+
+        self.out = nn.Sequential(normalization(ch), nn.SiLU(),
+                                 zero_module(conv_nd(dims, model_channels, out_channels, 3, padding=1)))
+        self.set_checkpointing(use_checkpoint)
+
+    def set_checkpointing(self, flag: bool, min_tokens: int = 0):
+        """Gradient checkpointing of ResBlocks and transformer blocks (the reference checkpoints all of them:
+        v1-inference.yaml:43, attention.py:224).  `min_tokens` keeps the activations of blocks whose feature map has
+        fewer pixels than that (cheap to store, so their recompute can be skipped on a 180 GB part)."""
+        self.use_checkpoint = bool(flag)
+        self.checkpoint_min_tokens = int(min_tokens)
+        for m in self.modules():
+            if isinstance(m, ResBlock):
+                m.use_checkpoint = bool(flag)
+                m.checkpoint_min_tokens = int(min_tokens)
+            elif isinstance(m, BasicTransformerBlock):
+                m.checkpoint = bool(flag)
+                m.checkpoint_min_tokens = int(min_tokens)
+
+    # -- per-prompt attention state (in-memory replacement of the reference's c{i}_*.pt files) ---------------
+    def transformer_blocks(self) -> Iterable[BasicTransformerBlock]:
+        for m in self.modules():
+            if isinstance(m, BasicTransformerBlock):
+                yield m
+
+    def set_local_contexts(self, local_contexts: Optional[Sequence[th.Tensor]], first_timestep: Optional[int] = None):
+        for blk in self.transformer_blocks():
+            blk.set_local_contexts(local_contexts)
+            if first_timestep is not None:
+                blk.first_timestep = first_timestep
+
+    def reset_attention_cache(self):
+        for blk in self.transformer_blocks():
+            blk.reset_cache()
+
+    def forward(self, x, text_index=None, timesteps=None, context=None, y=None, coef=None, bboxs_curr=None,
+                step_time: Optional[int] = None, **kwargs):
+        """x [2B,4,H,W], timesteps [2B], context [2B,77,768] -> eps [2B,4,H,W]   (reference :710-742)."""
+        assert y is None, "SD-v1 is not class-conditional"
+        hs = []
+        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels, repeat_only=False))
+        # the reference hands timesteps[0] (a device scalar) to every block, which then syncs on `time == 981`
+        # (attention.py:240); callers of this package pass the same value as a host int instead
+        time = step_time if step_time is not None else int(timesteps[0].item())  # one sync instead of 16
+        h = x.type(self.dtype)
+        for module in self.input_blocks:
+            h = module(h, emb, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
+            hs.append(h)
+        h = self.middle_block(h, emb, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
+        for module in self.output_blocks:
+            h = th.cat([h, hs.pop()], dim=1)
+            h = module(h, emb, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
+        h = h.type(x.dtype)
+        return self.out(h)

@@ -1,0 +1,181 @@
+"""GPU parity of the drop-in modules (diffusion_spacetime_attn_b200/ldm) — fp16 kernels under autocast — against
+(a) the CPU oracle in fp32 with the same seeded weights and (b) the committed outputs of the UNMODIFIED reference
+modules (tests/golden, made by oracle/make_golden.py).
+
+Tolerances: relative L2 error of a block / UNet output <= 5e-3; dL/dalpha relative error <= 2e-2;
+final latent of the 10-step trajectory: relative L2 <= 2e-2 (fp16 rounding amplified over 11 evaluations).
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from diffusion_spacetime_attn_b200 import native, ops
+from diffusion_spacetime_attn_b200.ldm.models.diffusion.ddpm import LatentDiffusion
+from diffusion_spacetime_attn_b200.ldm.models.diffusion.plms import PLMSSampler
+from diffusion_spacetime_attn_b200.ldm.modules.attention import BasicTransformerBlock, build_object_masks
+from diffusion_spacetime_attn_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+from oracle import sta_oracle as O
+
+GOLD = Path(__file__).resolve().parent / "golden"
+BBOXES = [[0.30, 0.50], [0.70, 0.50]]
+TINY = dict(attention_resolutions=(1, 2), num_res_blocks=1, channel_mult=(1, 2))
+
+
+def ctx_tensor(seed, shape=(1, 77, 768)):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * 1.04
+
+
+def uncond():
+    return torch.load(GOLD / "uncond_embedding.pt", map_location="cpu").float()
+
+
+def rel_l2(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).norm() / ref.norm()).item()
+
+
+@pytest.mark.gpu
+def test_masks_match_oracle_bit_for_bit():
+    for n in (64, 256, 1024, 4096, 9216):
+        ours = build_object_masks([[0.3, 0.5], [0.7, 0.5], [0.05, 0.95]], n, "cpu")
+        assert torch.equal(ours, O.flat_masks([[0.3, 0.5], [0.7, 0.5], [0.05, 0.95]], n))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,C,n_obj", [(4096, 320, 2), (1024, 640, 2), (256, 1280, 3), (64, 1280, 2), (1024, 640, 0)])
+def test_block_matches_oracle(n, C, n_obj):
+    blk = BasicTransformerBlock(C, 8, C // 8, context_dim=768)
+    shapes = {k: tuple(v.shape) for k, v in blk.state_dict().items()}
+    sd = O.seeded_state_dict(shapes, seed=2)
+    blk.load_state_dict(sd)
+    blk = blk.cuda().eval()
+    g = torch.Generator().manual_seed(n + C)
+    x = torch.randn(2, n, C, generator=g)
+    context = torch.cat([uncond(), ctx_tensor(100)])
+    local_cs = [ctx_tensor(101 + i) for i in range(n_obj)]
+    bboxes = [[0.3 + 0.2 * i, 0.4 + 0.1 * i] for i in range(n_obj)]
+    coef = torch.tensor([2.5, 1.5, 0.75][:n_obj])
+    ref = O.transformer_block(x, context, coef, [torch.cat([uncond(), c]) for c in local_cs],
+                              O.flat_masks(bboxes, n), sd, "", 8)
+    blk.set_local_contexts([c.cuda() for c in local_cs])
+    with torch.no_grad(), torch.autocast("cuda"):
+        y = blk(x.cuda().half(), context=context.cuda(), time=981, coef=coef.cuda(), bboxs_curr=bboxes)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    err = rel_l2(y, ref)
+    assert err < 5e-3, f"relative L2 error {err:.3e}"
+
+
+def _tiny_models(seed):
+    cfg = O.UNetConfig(**TINY)
+    sd = O.seeded_state_dict(O.unet_param_shapes(cfg), seed)
+    m = UNetModel(**TINY)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd, cfg
+
+
+@pytest.mark.gpu
+def test_tiny_unet_matches_reference_golden():
+    gold = np.load(GOLD / "unet_tiny.npz")
+    m, sd, cfg = _tiny_models(int(gold["seed"]))
+    g = torch.Generator().manual_seed(1)
+    lat = int(gold["latent"])
+    x = torch.randn(1, 4, lat, lat, generator=g)
+    context = torch.cat([uncond(), ctx_tensor(100)]).cuda()
+    m.set_local_contexts([ctx_tensor(101).cuda(), ctx_tensor(102).cuda()], first_timestep=981)
+    t = torch.full((2,), int(gold["t"]), dtype=torch.long, device="cuda")
+    with torch.no_grad(), torch.autocast("cuda"):
+        y = m(torch.cat([x, x]).cuda(), 0, t, context=context, coef=torch.tensor([2.5, 2.5]).cuda(), bboxs_curr=BBOXES,
+              step_time=int(gold["t"]))
+    err = rel_l2(y, torch.from_numpy(gold["eps"]))
+    assert native.device_error() == 0
+    assert err < 5e-3, f"relative L2 error vs reference output {err:.3e}"
+
+
+def _full_model():
+    sd = O.seeded_state_dict(O.unet_param_shapes(O.UNetConfig()), 0)
+    ld = LatentDiffusion(build_first_stage=False)
+    ld.model.diffusion_model.load_state_dict(sd, strict=True)
+    del sd
+    return ld.cuda().eval().requires_grad_(False)
+
+
+@pytest.mark.gpu
+def test_full_unet_and_config1_trajectory_match_reference_golden():
+    """SD-v1 UNet (859.5 M seeded weights): one evaluation, then BASELINE.json configs[0] (10 PLMS steps, fixed alpha)."""
+    f1, f2 = GOLD / "unet_full.npz", GOLD / "config1_trajectory.npz"
+    if not f1.exists():
+        pytest.skip("full-UNet fixture not generated")
+    ld = _full_model()
+    unet = ld.model.diffusion_model
+    gold = np.load(f1)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, 64, 64, generator=g)
+    uc, c = uncond().cuda(), ctx_tensor(100).cuda()
+    locs = [ctx_tensor(101).cuda(), ctx_tensor(102).cuda()]
+    unet.set_local_contexts(locs, first_timestep=981)
+    t = torch.full((2,), int(gold["t"]), dtype=torch.long, device="cuda")
+    with torch.no_grad(), torch.autocast("cuda"):
+        y = unet(torch.cat([x, x]).cuda(), 0, t, context=torch.cat([uc, c]), coef=torch.tensor([2.5, 2.5]).cuda(),
+                 bboxs_curr=BBOXES, step_time=int(gold["t"]))
+    err = rel_l2(y, torch.from_numpy(gold["eps"]))
+    assert err < 5e-3, f"single evaluation: relative L2 error vs reference output {err:.3e}"
+    if not f2.exists():
+        pytest.skip("trajectory fixture not generated")
+    traj = np.load(f2)
+    sampler = PLMSSampler(ld, clip_loss_model=torch.nn.Identity(), save_images=False)
+    with torch.autocast("cuda"):
+        sampler.sample(S=int(traj["steps"]), batch_size=1, shape=[4, 64, 64], conditioning=c, x_T=x.cuda(),
+                       unconditional_guidance_scale=7.5, unconditional_conditioning=uc, eta=0.0, text_index=0,
+                       curr_text="a red cube left of a blue sphere", bboxs_curr=BBOXES, seed=1, prompt_idx=0,
+                       object_names=["red cube", "blue sphere"], local_conditionings=locs, optimize_alpha=False)
+    err = rel_l2(sampler.last_result["latent"], torch.from_numpy(traj["latent"]))
+    assert native.device_error() == 0
+    assert err < 2e-2, f"10-step trajectory: relative L2 error vs reference-UNet trajectory {err:.3e}"
+
+
+@pytest.mark.gpu
+def test_alpha_gradient_matches_oracle_autograd():
+    """dL/dalpha through a 3-step PLMS trajectory (4 UNet evaluations) of the tiny UNet, L = <z_0, G>."""
+    m, sd, cfg = _tiny_models(5)
+    ld = LatentDiffusion(unet_config={"params": dict(TINY)}, build_first_stage=False)
+    ld.model.diffusion_model = m
+    ld = ld.cuda().eval().requires_grad_(False)
+    S, lat = 4, 16  # S must divide 1000
+    g = torch.Generator().manual_seed(3)
+    x_T = torch.randn(1, 4, lat, lat, generator=g)
+    G = torch.randn(1, 4, lat, lat, generator=g)
+    uc, c = uncond(), ctx_tensor(100)
+    locs = [ctx_tensor(101), ctx_tensor(102)]
+    # ---- oracle, fp32 CPU autograd ----
+    W_ref = torch.full((2, S), 2.5, requires_grad=True)
+    sch = O.make_schedule(S)
+
+    def eps_model(x, t, i):
+        return O.guided_eps(x, t, W_ref[:, i], uc, c, locs, uncond(), BBOXES, sd, cfg)
+
+    z_ref = O.plms_trajectory(eps_model, x_T, S, sch)
+    (z_ref * G).sum().backward()
+    # ---- product, fp16 kernels ----
+    sampler = PLMSSampler(ld, clip_loss_model=torch.nn.Identity(), save_images=False)
+    sampler.make_schedule(S, verbose=False)
+    m.set_local_contexts([t.cuda() for t in locs], first_timestep=int(sampler.ddim_timesteps[-1]))
+    W = torch.full((1, 2, S), 2.5, device="cuda", requires_grad=True)
+    for ckpt in (False, True):
+        m.set_checkpointing(ckpt)
+        W.grad = None
+        with torch.autocast("cuda"):
+            z = sampler._trajectory(x_T.cuda(), c.cuda(), uc.cuda(), 7.5, W, BBOXES, 0)
+            (z.float() * G.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        assert native.device_error() == 0
+        assert rel_l2(z, z_ref) < 1e-2
+        got, want = W.grad[0].cpu(), W_ref.grad
+        rel = ((got - want).abs() / (want.abs().max())).max().item()
+        assert rel < 2e-2, f"checkpoint={ckpt}: dL/dalpha rel err {rel:.3e}\n{got}\n{want}"
