@@ -20,6 +20,49 @@ def launch_count() -> int:
     return sum(LAUNCHES.values())
 
 
+# Optional per-launch device timing (bench.py turns it on for the timed region): CUDA events are recorded on the
+# launching stream right before / after every C-ABI call; `kernel_time_summary()` reduces them after a sync.
+_PROFILE = None
+
+
+def profile_start() -> None:
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_stop():
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    return rec or []
+
+
+class _timed:
+    def __init__(self, kind, key):
+        self.kind, self.key = kind, key
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.b.record()
+            _PROFILE.append((self.kind, self.key, self.a, self.b))
+        return False
+
+
+def kernel_time_summary(records):
+    """{(kind, key): (launches, total_ms)} from profile_stop() records; call after torch.cuda.synchronize()."""
+    out = {}
+    for kind, key, a, b in records:
+        n, t = out.get((kind, key), (0, 0.0))
+        out[(kind, key)] = (n + 1, t + a.elapsed_time(b))
+    return out
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -60,7 +103,8 @@ def sattn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     a.v_token_stride, a.v_batch_stride = _token_major(v, "v")
     a.o_token_stride, a.o_batch_stride = _token_major(out, "out")
     a.scale = scale
-    native.check(native.load().sta_sattn_fwd(C.byref(a), _stream()), "sta_sattn_fwd")
+    with _timed("sattn_fwd", (b, n, heads, d)):
+        native.check(native.load().sta_sattn_fwd(C.byref(a), _stream()), "sta_sattn_fwd")
     LAUNCHES["sattn_fwd"] += 1
     return out, lse
 
@@ -103,7 +147,8 @@ def xattn_fwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: O
     a.q_token_stride, a.q_batch_stride = _token_major(q, "q")
     a.o_token_stride, a.o_batch_stride = _token_major(out, "out")
     a.scale = scale
-    native.check(native.load().sta_xattn_fwd(C.byref(a), _stream()), "sta_xattn_fwd")
+    with _timed("xattn_fwd", (B, n, heads, d, n_obj)):
+        native.check(native.load().sta_xattn_fwd(C.byref(a), _stream()), "sta_xattn_fwd")
     LAUNCHES["xattn_fwd"] += 1
     return out, lse
 
@@ -132,7 +177,8 @@ def xattn_bwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: O
     a.q_token_stride, a.q_batch_stride = _token_major(q, "q")
     a.do_token_stride, a.do_batch_stride = _token_major(d_out, "d_out")
     a.scale = scale
-    native.check(native.load().sta_xattn_bwd(C.byref(a), _stream()), "sta_xattn_bwd")
+    with _timed("xattn_bwd", (B, n, heads, d, n_obj)):
+        native.check(native.load().sta_xattn_bwd(C.byref(a), _stream()), "sta_xattn_bwd")
     LAUNCHES["xattn_bwd"] += 1
     return d_q, d_coef
 
@@ -161,7 +207,8 @@ def sattn_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     a.o_token_stride, a.o_batch_stride = _token_major(out, "out")
     a.do_token_stride, a.do_batch_stride = _token_major(d_out, "d_out")
     a.scale = scale
-    native.check(native.load().sta_sattn_bwd(C.byref(a), _stream()), "sta_sattn_bwd")
+    with _timed("sattn_bwd", (b, n, heads, d)):
+        native.check(native.load().sta_sattn_bwd(C.byref(a), _stream()), "sta_sattn_bwd")
     LAUNCHES["sattn_bwd"] += 3  # delta, main, dq cast
     return d_qkv[0], d_qkv[1], d_qkv[2]
 
