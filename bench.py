@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--checkpoint_min_tokens", type=int, default=int(os.environ.get("STA_CKPT_MIN_TOKENS", "0")))
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graphs (block-level checkpointing, as the reference)")
     return ap.parse_args()
 
 
@@ -125,6 +126,48 @@ def launch_bytes(kind, key):
     B, n, h, d, n_obj = key
     C = h * d
     return 2 * (2 * B * n * C) * 2 + (2 + n_obj) * B * 77 * C * 2 * 2 + B * n_obj * n
+
+
+def standalone_kernel_ms(kind, key, iters=10):
+    """Mean device time of ONE launch of a sta_* kernel at the step's exact geometry: `iters` back-to-back launches
+    between two CUDA events on the launching stream, after a warm-up, with an L2 flush (256 MiB memset) before."""
+    import torch
+
+    from diffusion_spacetime_attn_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g).half()
+    if kind.startswith("sattn"):
+        b, n, h, d = key
+        q, k, v, do = rnd(b, n, h * d), rnd(b, n, h * d), rnd(b, n, h * d), rnd(b, n, h * d) * 0.1
+        out, lse = ops.sattn_fwd(q, k, v, h)
+        fn = (lambda: ops.sattn_fwd(q, k, v, h)) if kind == "sattn_fwd" else (lambda: ops.sattn_bwd(q, k, v, out, lse, do, h))
+    else:
+        B, n, h, d, n_obj = key
+        C = h * d
+        q, do = rnd(2 * B, n, C), rnd(2 * B, n, C) * 0.1
+        kc, vc = rnd(B, 2 + n_obj, 77, C), rnd(B, 2 + n_obj, 77, C)
+        mask = coef = None
+        if n_obj:
+            from diffusion_spacetime_attn_b200.ldm.modules.attention import build_object_masks
+
+            boxes = [[0.25 + 0.5 * (i % 2), 0.25 + 0.5 * ((i // 2) % 2)] for i in range(n_obj)]
+            mask = build_object_masks(boxes, n, "cuda").unsqueeze(0).expand(B, -1, -1).contiguous()
+            coef = torch.full((B, n_obj), 2.5, device="cuda")
+        out, lse = ops.xattn_fwd(q, kc, vc, mask, coef, h)
+        fn = (lambda: ops.xattn_fwd(q, kc, vc, mask, coef, h)) if kind == "xattn_fwd" else (
+            lambda: ops.xattn_bwd(q, kc, vc, mask, coef, lse, do, h))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        fn()
+    flush.zero_()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b_.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b_) / iters
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -209,7 +252,7 @@ def run_native(args):
 
     pipe = SpaceTimeAttnPipeline(device=f"cuda:{local_rank}", seed=0, steps=args.ddim_steps, num_epochs=args.epochs,
                                  use_checkpoint=True, checkpoint_min_tokens=args.checkpoint_min_tokens,
-                                 save_images=False)
+                                 save_images=False, cuda_graphs=not args.eager, half_weights=not args.eager)
     bcast_bytes = broadcast_weights(pipe.model) + (broadcast_weights(pipe.clip_loss) if world > 1 else 0)
 
     total_images = args.warmup + 2 * args.steps
@@ -237,7 +280,11 @@ def run_native(args):
     torch.cuda.reset_peak_memory_stats()
     barrier()
     launches0 = ops.launch_count()
-    ops.profile_start()
+    runner = pipe.model.graph_runner
+    if runner is not None:
+        runner.reset_counters()
+    else:
+        ops.profile_start()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -246,7 +293,8 @@ def run_native(args):
     ev1.record()
     barrier()
     clocks = sampler.stop()
-    records_k = ops.profile_stop()
+    records_k = ops.profile_stop() if runner is None else []
+    hist_graph = runner.launch_histogram() if runner is not None else None
     dev_ms = ev0.elapsed_time(ev1)
     launches = ops.launch_count() - launches0
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
@@ -272,13 +320,22 @@ def run_native(args):
     dev_ms, e2e_ms = float(times[0]), float(times[1])
     err = native.device_error()
 
-    # ---- per-kernel device time inside timed region 1 (rank-local) ----
-    summ = ops.kernel_time_summary(records_k)
+    # ---- per-kernel device time of the sta_* kernels launched inside timed region 1 (rank-local) ----
+    # Eager mode: CUDA events around every launch.  CUDA-graph mode (default): launches inside a replay cannot be
+    # bracketed by events, so the launch histogram of the replayed graphs is combined with the mean launch time of
+    # each (kernel, geometry) measured right here, standalone, on the same stream (back-to-back launches).
     kernels = []
-    for (kind, key), (n, tot) in summ.items():
-        kernels.append({"kernel": "sta_" + kind, "geometry": list(key), "launches": n, "total_ms": tot,
-                        "mean_us": 1000.0 * tot / n, "tflops": launch_flops(kind, key) / (tot / n) / 1e9,
-                        "gbs": launch_bytes(kind, key) / (tot / n) / 1e6})
+    if hist_graph:
+        for (kind, key), n in hist_graph.items():
+            ms = standalone_kernel_ms(kind, key)
+            kernels.append({"kernel": "sta_" + kind, "geometry": list(key), "launches": n, "total_ms": ms * n,
+                            "mean_us": 1000.0 * ms, "tflops": launch_flops(kind, key) / ms / 1e9,
+                            "gbs": launch_bytes(kind, key) / ms / 1e6, "timing": "standalone x launches"})
+    else:
+        for (kind, key), (n, tot) in ops.kernel_time_summary(records_k).items():
+            kernels.append({"kernel": "sta_" + kind, "geometry": list(key), "launches": n, "total_ms": tot,
+                            "mean_us": 1000.0 * tot / n, "tflops": launch_flops(kind, key) / (tot / n) / 1e9,
+                            "gbs": launch_bytes(kind, key) / (tot / n) / 1e6, "timing": "events in step"})
     kernels.sort(key=lambda r: -r["total_ms"])
     peaks = measured_peaks()
     traffic = None
@@ -304,7 +361,8 @@ def run_native(args):
                                    "alpha inner-opt on (%d epochs), batch=1 per GPU" % (args.ddim_steps, args.epochs),
                        "weights": pipe.weights, "prompts": "synthetic_gpt.txt (gpt.txt record format)",
                        "l2": "inputs larger than L2: each step streams ~3.4 GB of weights 300+ times",
-                       "gradient_checkpointing": "blocks with >= %d tokens" % args.checkpoint_min_tokens,
+                       "execution": ("CUDA graphs per UNet evaluation (fwd graph + recompute/bwd graph), fp16 weights"
+                                     if pipe.cuda_graphs else "eager, block-level gradient checkpointing"),
                        "parallelism": "dp%d (prompt-sharded, weights broadcast once: %d bytes)" % (world, bcast_bytes)},
             "e2e": {"value": n_img / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},

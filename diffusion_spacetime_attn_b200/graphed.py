@@ -1,0 +1,189 @@
+"""CUDA-graph execution of one UNet evaluation (forward, and forward+backward) for the alpha-optimisation loop.
+
+Why: a 512x512 image costs 3 x 51 UNet evaluations forward AND backward (reference plms.py:220-277).  In eager mode
+one evaluation is >1000 kernel launches and the GPU idles behind the Python/launch overhead (first measurement on
+B200: ~100 ms per evaluation triple, ~6x the device time).  The reference's answer to memory — gradient
+checkpointing of every block (util.py:102-148) — is kept in spirit but moved to evaluation granularity, which makes
+both halves graph-capturable:
+
+  forward sweep   eps_i = G_fwd(x_i, t_i, coef_i)            no autograd state kept; replay of ONE captured graph
+  backward sweep  (dx_i, dcoef_i) = G_bwd(x_i, t_i, coef_i, d_eps_i)   recompute + backward of evaluation i in ONE graph
+
+The arithmetic per image is the same as block-level checkpointing (2 forwards + 1 backward per evaluation) but there
+is no per-block recompute bookkeeping and no launch overhead; the activations of a single evaluation live in the
+graph's private pool and are reused by all 153 evaluations.  The sm_100a attention kernels are captured like any other
+launch (the C ABI enqueues on the current stream, allocates nothing and never syncs).
+
+Static state: inputs are copied into fixed buffers before a replay; the per-prompt attention caches (projected context
+K/V, masks) are fixed buffers too, refreshed in place by BasicTransformerBlock._build_cache.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+class GraphedUNetEval:
+    """Captured graphs of `unet` for a fixed (batch, n_obj, latent) signature."""
+
+    def __init__(self, unet, batch2: int, n_obj: int, latent_hw: Tuple[int, int], ctx_shape=(77, 768), warmup: int = 2):
+        self.unet = unet
+        dev = next(unet.parameters()).device
+        h, w = latent_hw
+        B = batch2 // 2
+        self.B, self.n_obj = B, n_obj
+        self.x = torch.zeros(batch2, 4, h, w, device=dev, dtype=torch.float32)
+        self.t = torch.zeros(batch2, device=dev, dtype=torch.long)
+        self.coef = torch.zeros(B, max(n_obj, 1), device=dev, dtype=torch.float32)[:, :n_obj].contiguous()
+        self.d_eps = torch.zeros(batch2, 4, h, w, device=dev, dtype=torch.float32)
+        self.context = torch.zeros(batch2, *ctx_shape, device=dev, dtype=torch.float32)
+        self.bboxes = None
+        self.g_fwd = self.g_bwd = None
+        self.eps = self.dx = self.dcoef = None
+        self.launches_fwd = self.launches_bwd = 0
+        self.trace_fwd, self.trace_bwd = [], []   # (kind, geometry) of the sta_* launches inside each graph
+        self.replays_fwd = self.replays_bwd = 0
+        self.warmup = warmup
+
+    # ------------------------------------------------------------------------------------------------
+    def _eval(self, x, coef):
+        with torch.autocast("cuda", dtype=torch.float16):
+            # step_time = -1: never equal to a schedule timestep, so no block rebuilds its cache inside a capture
+            return self.unet(x, 0, self.t, context=self.context, coef=coef if self.n_obj else None,
+                             bboxs_curr=self.bboxes, step_time=-1).float()
+
+    def capture(self, bboxes) -> None:
+        """Warm up on a side stream, then capture the forward-only and the forward+backward graphs."""
+        self.bboxes = bboxes
+        with torch.enable_grad():
+            self._capture()
+
+    def _capture(self) -> None:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self.warmup):
+                with torch.no_grad():
+                    self._eval(self.x, self.coef)
+                xg = self.x.detach().requires_grad_(True)
+                cg = self.coef.detach().requires_grad_(True)
+                eps = self._eval(xg, cg)
+                torch.autograd.grad(eps, [xg] + ([cg] if self.n_obj else []), self.d_eps)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+
+        n0 = ops.launch_count()
+        ops.trace_start()
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd):
+            with torch.no_grad():
+                self.eps = self._eval(self.x, self.coef)
+        self.launches_fwd = ops.launch_count() - n0
+        self.trace_fwd = ops.trace_stop()
+
+        n0 = ops.launch_count()
+        ops.trace_start()
+        self.g_bwd = torch.cuda.CUDAGraph()
+        self._xg = self.x.detach().requires_grad_(True)
+        self._cg = self.coef.detach().requires_grad_(True)
+        with torch.cuda.graph(self.g_bwd):
+            # inputs are read from the static buffers at replay time (x/coef share storage with _xg/_cg)
+            eps = self._eval(self._xg, self._cg)
+            grads = torch.autograd.grad(eps, [self._xg] + ([self._cg] if self.n_obj else []), self.d_eps)
+            self.dx = grads[0]
+            self.dcoef = grads[1] if self.n_obj else None
+        self.launches_bwd = ops.launch_count() - n0
+        self.trace_bwd = ops.trace_stop()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------------------------------------
+    def set_context(self, context: torch.Tensor) -> None:
+        self.context.copy_(context)
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, coef: Optional[torch.Tensor]) -> torch.Tensor:
+        self.x.copy_(x)
+        self.t.copy_(t)
+        if self.n_obj:
+            self.coef.copy_(coef.reshape(self.B, self.n_obj))
+        self.g_fwd.replay()
+        self.replays_fwd += 1
+        ops.LAUNCHES["graph_replayed"] = ops.LAUNCHES.get("graph_replayed", 0) + self.launches_fwd
+        return self.eps.clone()
+
+    def backward(self, x, t, coef, d_eps):
+        self.x.copy_(x)
+        self.t.copy_(t)
+        if self.n_obj:
+            self.coef.copy_(coef.reshape(self.B, self.n_obj))
+        self.d_eps.copy_(d_eps)
+        self.g_bwd.replay()
+        self.replays_bwd += 1
+        ops.LAUNCHES["graph_replayed"] = ops.LAUNCHES.get("graph_replayed", 0) + self.launches_bwd
+        return self.dx.clone(), (self.dcoef.clone() if self.n_obj else None)
+
+
+class _GraphedEvalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, coef, t, runner: GraphedUNetEval):
+        ctx.runner = runner
+        ctx.has_coef = coef is not None
+        ctx.save_for_backward(x, t, coef if coef is not None else x.new_zeros(0))
+        return runner.forward(x, t, coef)
+
+    @staticmethod
+    def backward(ctx, d_eps):
+        x, t, coef = ctx.saved_tensors
+        dx, dcoef = ctx.runner.backward(x, t, coef if ctx.has_coef else None, d_eps)
+        if ctx.has_coef and dcoef is not None:
+            dcoef = dcoef.reshape(coef.shape)
+        return dx, (dcoef if ctx.has_coef else None), None, None
+
+
+class GraphedModelRunner:
+    """Keeps one GraphedUNetEval per (batch, n_obj, latent) signature and routes apply_model_extra through it."""
+
+    def __init__(self, unet):
+        self.unet = unet
+        self.graphs: Dict[tuple, GraphedUNetEval] = {}
+        self.active: Optional[GraphedUNetEval] = None
+
+    def begin_prompt(self, x_shape, context, local_contexts, bboxes, first_timestep: int) -> None:
+        """Refresh the static per-prompt state (context K/V caches, masks) and select / capture the graph."""
+        batch2 = 2 * x_shape[0]
+        n_obj = len(local_contexts) if local_contexts is not None else 0
+        key = (batch2, n_obj, x_shape[2], x_shape[3])
+        unet = self.unet
+        unet.set_local_contexts(local_contexts, first_timestep=first_timestep)
+        g = self.graphs.get(key)
+        fresh = g is None
+        if fresh:
+            g = GraphedUNetEval(unet, batch2, n_obj, (x_shape[2], x_shape[3]), tuple(context.shape[1:]))
+        g.set_context(context)
+        g.bboxes = bboxes
+        # (re)build every block's cache in place from the new context / local embeddings / layout
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            for blk in unet.transformer_blocks():
+                blk.refresh_cache(g.context, bboxes, batch2)
+        if fresh:
+            g.capture(bboxes)
+            self.graphs[key] = g
+        self.active = g
+
+    def __call__(self, x_in, t_in, coef):
+        return _GraphedEvalFn.apply(x_in, coef, t_in, self.active)
+
+    def launch_histogram(self):
+        """{(kind, geometry): launches} of the sta_* kernels replayed so far (all signatures)."""
+        hist = {}
+        for g in self.graphs.values():
+            for trace, n in ((g.trace_fwd, g.replays_fwd), (g.trace_bwd, g.replays_bwd)):
+                for kk in trace:
+                    hist[kk] = hist.get(kk, 0) + n
+        return hist
+
+    def reset_counters(self):
+        for g in self.graphs.values():
+            g.replays_fwd = g.replays_bwd = 0

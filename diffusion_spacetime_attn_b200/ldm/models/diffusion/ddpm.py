@@ -53,6 +53,7 @@ class LatentDiffusion(nn.Module):
             fs = (first_stage_config or {"params": V1_VAE})
             self.first_stage_model = AutoencoderKL(**fs.get("params", fs)).eval().requires_grad_(False)
         self.cond_stage_model = cond_stage_model
+        self.graph_runner = None  # graphed.GraphedModelRunner when CUDA-graph execution is enabled
         self.register_schedule(timesteps=timesteps, linear_start=linear_start, linear_end=linear_end)
 
     def register_schedule(self, beta_schedule="linear", timesteps=1000, linear_start=1e-4, linear_end=2e-2):
@@ -82,6 +83,8 @@ class LatentDiffusion(nn.Module):
 
     def apply_model_extra(self, x_noisy, text_index, t, cond, return_ids=False, coef=None, bboxs_curr=None,
                           step_time=None):
+        if self.graph_runner is not None and self.graph_runner.active is not None:
+            return self.graph_runner(x_noisy, t, coef)  # context / layout were fixed by begin_prompt()
         if not isinstance(cond, dict):
             cond = {"c_crossattn": cond if isinstance(cond, list) else [cond]}
         return self.model(x_noisy, text_index, t, **cond, coef=coef, bboxs_curr=bboxs_curr, step_time=step_time)

@@ -143,8 +143,13 @@ class PLMSSampler(object):
         S = len(self.ddim_timesteps)
 
         unet = self.model.model.diffusion_model
-        unet.set_local_contexts(local_conditionings, first_timestep=int(self.ddim_timesteps[-1]))
         bboxes_arg = bboxes_pp if B > 1 else bboxes_pp[0]
+        runner = getattr(self.model, "graph_runner", None)
+        if runner is not None:  # CUDA-graph execution: fix the per-prompt state once, capture on first use
+            runner.begin_prompt(shape, torch.cat([unconditional_conditioning, cond]), local_conditionings, bboxes_arg,
+                                first_timestep=int(self.ddim_timesteps[-1]))
+        else:
+            unet.set_local_contexts(local_conditionings, first_timestep=int(self.ddim_timesteps[-1]))
 
         if n_obj:
             W = torch.full((B, n_obj, S), self.weight_initialize_coef / n_obj, device=device, dtype=torch.float32)
@@ -174,6 +179,8 @@ class PLMSSampler(object):
                     losses.append([float(v) for v in torch.stack(per_prompt).detach().cpu()])
             if epoch == epochs - 1 and self.save_images and decoded is not None:
                 self._save(decoded.detach(), epoch if do_opt else 2, seed, idxs)
+        if runner is not None:
+            runner.active = None
         unet.set_local_contexts(None)
         self.last_result = {"latent": img.detach(), "weighting_parameter": W.detach(), "losses": losses,
                             "image": decoded.detach() if decoded is not None else None}

@@ -23,6 +23,18 @@ def launch_count() -> int:
 # Optional per-launch device timing (bench.py turns it on for the timed region): CUDA events are recorded on the
 # launching stream right before / after every C-ABI call; `kernel_time_summary()` reduces them after a sync.
 _PROFILE = None
+_TRACE = None  # when a list: (kind, geometry) of every launch, no events (usable during CUDA-graph capture)
+
+
+def trace_start() -> None:
+    global _TRACE
+    _TRACE = []
+
+
+def trace_stop():
+    global _TRACE
+    rec, _TRACE = _TRACE, None
+    return rec or []
 
 
 def profile_start() -> None:
@@ -41,6 +53,8 @@ class _timed:
         self.kind, self.key = kind, key
 
     def __enter__(self):
+        if _TRACE is not None:
+            _TRACE.append((self.kind, self.key))
         if _PROFILE is not None:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)

@@ -108,7 +108,8 @@ class SpaceTimeAttnPipeline:
     def __init__(self, device="cuda", ckpt: Optional[str] = None, seed: int = 0, steps: int = 50, scale: float = 7.5,
                  latent_size: int = 64, sampler: str = "plms", use_checkpoint: bool = True,
                  checkpoint_min_tokens: int = 0, num_epochs: int = 3, save_images: bool = False,
-                 out_dir: str = "result_outputs", with_vae: bool = True, unet_config: Optional[dict] = None):
+                 out_dir: str = "result_outputs", with_vae: bool = True, unet_config: Optional[dict] = None,
+                 cuda_graphs: bool = True, half_weights: bool = True):
         from . import native
 
         native.load()  # fail loudly before building 4 GB of networks if the CUDA library is missing
@@ -128,7 +129,22 @@ class SpaceTimeAttnPipeline:
             randomize_zero_modules(self.model, seed=seed)
             self.weights = f"seeded-random(seed={seed})"
         self.model.to(self.device).eval().requires_grad_(False)
-        self.model.model.diffusion_model.set_checkpointing(use_checkpoint, checkpoint_min_tokens)
+        unet = self.model.model.diffusion_model
+        if half_weights:
+            # fp16 conv/linear weights, fp32 norms: numerically what torch.autocast computes from fp32 masters
+            # (scripts/txt2img-gpt.py:310), without re-casting 3.4 GB of weights on every evaluation
+            unet.half()
+            for m in unet.modules():
+                if isinstance(m, (torch.nn.GroupNorm, torch.nn.LayerNorm)):
+                    m.float()
+        self.cuda_graphs = cuda_graphs
+        if cuda_graphs:
+            from .graphed import GraphedModelRunner
+
+            unet.set_checkpointing(False)  # evaluation-level recompute lives in graphed.py
+            self.model.graph_runner = GraphedModelRunner(unet)
+        else:
+            unet.set_checkpointing(use_checkpoint, checkpoint_min_tokens)
         self.text = SyntheticTextEmbedder(device="cpu")
         self.model.cond_stage_model = self.text
         self.clip_loss = DCLIPLoss(device=self.device, seed=seed + 1) if with_vae else torch.nn.Identity()
