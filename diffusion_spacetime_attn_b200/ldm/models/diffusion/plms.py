@@ -43,7 +43,7 @@ class PLMSSampler(object):
 
     def __init__(self, model, schedule="linear", clip_loss_model=None, num_epochs=3, lr=0.005,
                  weight_initialize_coef=5.0, local_loss_weight=5.0, save_images=True, out_dir="result_outputs",
-                 verbose=False, **kwargs):
+                 verbose=False, loss_fn=None, decode_fn=None, **kwargs):
         super().__init__()
         self.model = model
         self.ddpm_num_timesteps = model.num_timesteps
@@ -57,6 +57,9 @@ class PLMSSampler(object):
         self.num_epochs, self.lr = num_epochs, lr
         self.weight_initialize_coef, self.local_loss_weight = weight_initialize_coef, local_loss_weight
         self.save_images, self.out_dir, self.verbose = save_images, out_dir, verbose
+        # test hooks: replace the VAE decode / CLIP loss by any differentiable stand-ins (both are outside the kernels)
+        self.loss_fn = loss_fn or self._loss
+        self.decode_fn = decode_fn or (lambda z: torch.clamp((self.model.decode_first_stage(z) + 1.0) / 2.0, 0.0, 1.0))
         self.last_result = None
 
     # ------------------------------------------------------------------------------------------------
@@ -169,10 +172,9 @@ class PLMSSampler(object):
                 img = self._trajectory(img_input.clone(), cond, unconditional_conditioning,
                                        unconditional_guidance_scale, W if n_obj else None, bboxes_arg, text_index)
                 if do_opt or self.save_images:
-                    decoded = self.model.decode_first_stage(img)
-                    decoded = torch.clamp((decoded + 1.0) / 2.0, min=0.0, max=1.0)
+                    decoded = self.decode_fn(img)  # (decode + 1) / 2 clamped to [0, 1]   (plms.py:249-250)
                 if do_opt:
-                    loss, per_prompt = self._loss(decoded, texts, bboxes_pp, names_pp)
+                    loss, per_prompt = self.loss_fn(decoded, texts, bboxes_pp, names_pp)
                     optimizer.zero_grad(set_to_none=True)
                     loss.backward()
                     optimizer.step()

@@ -179,3 +179,55 @@ def test_alpha_gradient_matches_oracle_autograd():
         got, want = W.grad[0].cpu(), W_ref.grad
         rel = ((got - want).abs() / (want.abs().max())).max().item()
         assert rel < 2e-2, f"checkpoint={ckpt}: dL/dalpha rel err {rel:.3e}\n{got}\n{want}"
+
+
+@pytest.mark.gpu
+def test_cuda_graph_execution_matches_eager_alpha_optimisation():
+    """Two alpha epochs of a 4-step trajectory on the tiny UNet: CUDA-graph execution (fp16 weights, evaluation-level
+    recompute) must reproduce the eager, block-checkpointed path (fp32 masters under autocast): same latents, same
+    optimised weights, and a second prompt must reuse the captured graphs with refreshed contexts."""
+    from diffusion_spacetime_attn_b200.graphed import GraphedModelRunner
+
+    S, lat = 4, 16
+    g = torch.Generator().manual_seed(8)
+    G = torch.randn(1, 4, lat, lat, generator=g).cuda()
+    loss_fn = lambda imgs, *a: ((imgs.float() * G).sum(), [(imgs.float() * G).sum()])
+    results = {}
+    for mode in ("eager", "graph"):
+        m, sd, cfg = _tiny_models(5)
+        ld = LatentDiffusion(unet_config={"params": dict(TINY)}, build_first_stage=False)
+        ld.model.diffusion_model = m
+        ld = ld.cuda().eval().requires_grad_(False)
+        if mode == "graph":
+            m.half()
+            for mod in m.modules():
+                if isinstance(mod, (torch.nn.GroupNorm, torch.nn.LayerNorm)):
+                    mod.float()
+            m.set_checkpointing(False)
+            ld.graph_runner = GraphedModelRunner(m)
+        else:
+            m.set_checkpointing(True)
+        sampler = PLMSSampler(ld, clip_loss_model=torch.nn.Identity(), save_images=False, num_epochs=2, lr=0.05,
+                              loss_fn=loss_fn, decode_fn=lambda z: z)
+        outs = []
+        for prompt_seed in (100, 200):  # two prompts: the second one replays the graphs captured for the first
+            x_T = torch.randn(1, 4, lat, lat, generator=torch.Generator().manual_seed(prompt_seed)).cuda()
+            with torch.autocast("cuda"):
+                sampler.sample(S=S, batch_size=1, shape=[4, lat, lat], conditioning=ctx_tensor(prompt_seed).cuda(),
+                               x_T=x_T, unconditional_guidance_scale=7.5, unconditional_conditioning=uncond().cuda(),
+                               text_index=0, curr_text="p", bboxs_curr=[[0.3, 0.5], [0.6 + prompt_seed / 2000, 0.5]],
+                               seed=1, prompt_idx=0, object_names=["a", "b"],
+                               local_conditionings=[ctx_tensor(prompt_seed + 1).cuda(), ctx_tensor(prompt_seed + 2).cuda()])
+            outs.append((sampler.last_result["latent"].float().cpu(), sampler.last_result["weighting_parameter"].cpu(),
+                         sampler.last_result["losses"]))
+        results[mode] = outs
+        if mode == "graph":
+            assert len(ld.graph_runner.graphs) == 1, "the second prompt must reuse the captured graphs"
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    for (z_e, w_e, l_e), (z_g, w_g, l_g) in zip(results["eager"], results["graph"]):
+        assert rel_l2(z_g, z_e) < 1e-2
+        dw_e = w_e - 2.5  # the Adam updates (initial value 5 / n_obj = 2.5)
+        assert (w_g - w_e).abs().max().item() < 0.1 * dw_e.abs().max().item() + 1e-4
+        assert abs(l_g[0][0] - l_e[0][0]) < 2e-2 * abs(l_e[0][0]) + 1e-2
+    assert (results["graph"][0][0] - results["graph"][1][0]).abs().max() > 1e-2  # different prompts, different latents
