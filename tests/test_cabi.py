@@ -1,0 +1,87 @@
+"""CPU: libsta_b200.so loads and exports every symbol include/sta_b200.h declares (no compute without a GPU), and the
+ctypes structs agree with the header's field lists."""
+from __future__ import annotations
+
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = (ROOT / "include" / "sta_b200.h").read_text()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from diffusion_spacetime_attn_b200 import native
+
+    return ctypes.CDLL(str(native.LIB_PATH))
+
+
+def declared_functions():
+    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(sta_\w+)\(", HEADER, flags=re.M)))
+
+
+def test_header_declares_the_documented_entry_points():
+    from diffusion_spacetime_attn_b200 import native
+
+    assert declared_functions() == sorted(native.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} is declared in include/sta_b200.h but not exported"
+
+
+def test_version_and_error_string(lib):
+    lib.sta_version.restype = ctypes.c_int
+    lib.sta_last_error.restype = ctypes.c_char_p
+    m = re.search(r"#define STA_B200_VERSION (\d+)", HEADER)
+    assert lib.sta_version() == int(m.group(1))
+    assert isinstance(lib.sta_last_error(), bytes)
+
+
+def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
+    from diffusion_spacetime_attn_b200 import native
+
+    for fn, argt in (("sta_sattn_fwd", native.SattnFwdArgs), ("sta_xattn_fwd", native.XattnFwdArgs),
+                     ("sta_sattn_bwd", native.SattnBwdArgs), ("sta_xattn_bwd", native.XattnBwdArgs)):
+        f = getattr(lib, fn)
+        f.argtypes = [ctypes.POINTER(argt), ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        assert f(ctypes.byref(argt()), None) == 1  # STA_ERR_BAD_ARG
+        lib.sta_last_error.restype = ctypes.c_char_p
+        assert b"null pointer" in lib.sta_last_error()
+
+
+@pytest.mark.parametrize("struct,cname", [("SattnFwdArgs", "sta_sattn_fwd_args"), ("SattnBwdArgs", "sta_sattn_bwd_args"),
+                                          ("XattnFwdArgs", "sta_xattn_fwd_args"), ("XattnBwdArgs", "sta_xattn_bwd_args"),
+                                          ("ProbeArgs", "sta_probe_args")])
+def test_ctypes_structs_mirror_the_header(struct, cname):
+    from diffusion_spacetime_attn_b200 import native
+
+    body = re.search(r"typedef struct \{([^{}]*)\} " + cname + ";", HEADER, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(void|float|uint8_t|int32_t|int64_t|uint32_t|uint64_t)\s*\*?\s*", "", decl)
+        for part in decl.split(","):
+            names.append(re.sub(r"\[.*\]", "", part).replace("*", "").strip())
+    assert names == [f[0] for f in getattr(native, struct)._fields_]
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+
+    from diffusion_spacetime_attn_b200 import ops
+
+    q = torch.zeros(1, 16, 320, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.sattn_fwd(q, q, q, heads=8)

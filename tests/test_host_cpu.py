@@ -1,0 +1,120 @@
+"""CPU: host-side logic of the drop-in (schedules, masks, prompt readers, sharding, sampler arithmetic) against the
+oracle and against closed forms.  No CUDA needed."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from diffusion_spacetime_attn_b200 import prompts as P
+from diffusion_spacetime_attn_b200.ldm.modules.attention import build_object_masks
+from diffusion_spacetime_attn_b200.ldm.modules.diffusionmodules import util as U
+from diffusion_spacetime_attn_b200.pipeline import WorkItem, shard_prompts, synthetic_layout
+from oracle import sta_oracle as O
+
+
+@pytest.mark.parametrize("S", [10, 50, 100])
+def test_schedule_matches_oracle(S):
+    betas = U.make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.012)
+    acp = np.cumprod(1.0 - betas).astype(np.float32)
+    ts = U.make_ddim_timesteps("uniform", S, 1000, verbose=False)
+    sig, a, ap = U.make_ddim_sampling_parameters(acp, ts, 0.0, verbose=False)
+    sch = O.make_schedule(S)
+    assert np.array_equal(ts, sch.timesteps) and ts[-1] == 1000 // S * (S - 1) + 1
+    assert np.array_equal(a, sch.alphas) and np.array_equal(ap, sch.alphas_prev) and not sig.any()
+    if S == 50:
+        assert ts[-1] == 981  # the constant the reference hard-codes (attention.py:240)
+
+
+def test_timestep_embedding_matches_oracle():
+    t = torch.tensor([1, 501, 981])
+    assert torch.equal(U.timestep_embedding(t, 320), O.timestep_embedding(t, 320))
+
+
+@pytest.mark.parametrize("n", [64, 144, 256, 1024, 4096, 9216])
+def test_masks_match_oracle_and_reference_semantics(n):
+    boxes = [[0.30, 0.50], [0.70, 0.50], [0.0, 1.0]]
+    m = build_object_masks(boxes, n, "cpu")
+    assert torch.equal(m, O.flat_masks(boxes, n))
+    dim = int(n ** 0.5)
+    r, c = int(0.5 * dim), int(0.3 * dim)
+    assert m[0, r * dim + c] == 1  # the disc centre: x indexes columns, y rows (attention.py:254-261)
+    assert m[0].sum() > 0 and m[0].sum() < 0.2 * n  # pi * 0.2^2 = 12.6 % of the latent
+
+
+def test_plms_closed_form_for_constant_eps():
+    """With eps == const every Adams-Bashforth combination returns that constant, so the trajectory is the DDIM
+    closed form x_0 = x_T * prod(sqrt(a_prev/a_t)) + e * sum(...): checks the multistep coefficients sum to 1."""
+    S = 10
+    sch = O.make_schedule(S)
+    e = torch.full((1, 4, 8, 8), 0.3)
+    x = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(0))
+    z = O.plms_trajectory(lambda xx, t, i: e, x, S, sch)
+    ref = x.clone()
+    for index in reversed(range(S)):
+        a_t, a_p = float(sch.alphas[index]), float(sch.alphas_prev[index])
+        pred = (ref - (1 - a_t) ** 0.5 * e) / a_t ** 0.5
+        ref = a_p ** 0.5 * pred + (1 - a_p) ** 0.5 * e
+    assert (z - ref).abs().max() < 1e-5
+
+
+def test_product_sampler_arithmetic_matches_oracle_on_cpu():
+    """PLMSSampler's update/combination code (no UNet involved) against the oracle's restatement."""
+    from diffusion_spacetime_attn_b200.ldm.models.diffusion.plms import PLMSSampler
+
+    class FakeModel:
+        num_timesteps = 1000
+        device = torch.device("cpu")
+        alphas_cumprod = torch.tensor(np.cumprod(1.0 - U.make_beta_schedule("linear", 1000, 0.00085, 0.012)), dtype=torch.float32)
+
+        def apply_model_extra(self, x_in, text_index, t_in, c_in, coef=None, bboxs_curr=None, step_time=None):
+            # a linear "UNet" whose output depends on x, t and coef, so every code path is exercised
+            s = (t_in.float() / 1000.0).reshape(-1, 1, 1, 1)
+            k = 1.0 + (coef.sum() if coef is not None else 0.0) * 0.01
+            return 0.1 * k * x_in * s + 0.05 * torch.cat([torch.zeros_like(x_in[:1]), torch.ones_like(x_in[1:])])
+
+    S = 10
+    sampler = PLMSSampler(FakeModel(), clip_loss_model=torch.nn.Identity(), save_images=False)
+    sampler.make_schedule(S, verbose=False)
+    x_T = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(1))
+    W = torch.full((1, 2, S), 2.5)
+    z = sampler._trajectory(x_T.clone(), torch.zeros(1, 77, 768), torch.zeros(1, 77, 768), 7.5, W, [[0.3, 0.5], [0.7, 0.5]], 0)
+
+    def eps_model(x, t, i):
+        out = FakeModel().apply_model_extra(torch.cat([x, x]), 0, torch.full((2,), t), None, coef=W[0, :, i])
+        e_u, e_c = out.chunk(2)
+        return e_u + 7.5 * (e_c - e_u)
+
+    z_ref = O.plms_trajectory(eps_model, x_T, S)
+    assert (z - z_ref).abs().max() < 1e-4
+
+
+def test_prompt_readers_and_layout():
+    recs = P.read_gpt(P.SYNTHETIC_GPT)
+    assert recs[0] == ("a red cube left of a blue sphere", ["red cube", "blue sphere"])  # BASELINE.json configs[0]
+    assert all(2 <= len(o) <= 3 for _, o in recs)
+    items = P.build_work_items(recs, start=10)
+    assert items[0].prompt_idx == 10 and items[0].seed == 1
+    for it in items:
+        assert len(it.bboxes) == len(it.object_names)
+        assert all(0.0 <= v <= 1.0 for b in it.bboxes for v in b)
+    lay = {recs[0][0]: {"silver bed": [0.574, 0.503], "white couch": [0.269, 0.442]}}  # README.md:56-62 format
+    it = P.build_work_items(recs[:1], layouts=lay)[0]
+    assert it.object_names == ["silver bed", "white couch"] and it.bboxes[0] == [0.574, 0.503]
+    assert synthetic_layout(["a", "b"], "p") == synthetic_layout(["a", "b"], "p")
+    assert P.guess_objects("The bed is below the cat.", 2) == ["bed", "cat"]
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_sharding_is_a_partition_with_global_indices(world):
+    n = 37
+    shards = [shard_prompts(n, r, world) for r in range(world)]
+    flat = sorted(i for s in shards for i in s)
+    assert flat == list(range(n))
+    assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+
+
+def test_object_crop_box_matches_reference_expression():
+    assert O.object_crop_box([0.3, 0.5]) == (int(512 * 0.3), int(512 * 0.7), int(512 * (0.3 - 0.2)), int(512 * 0.5))
+    assert O.object_crop_box([0.05, 0.95]) == (int(512 * 0.75), 512, 0, int(512 * 0.25))
+    assert float(O.alpha_init(2, 50)[0, 0]) == 2.5 and tuple(O.alpha_init(3, 10).shape) == (3, 10)

@@ -9,6 +9,8 @@ from diffusion_spacetime_attn_b200 import prompts as P
 pipe = SpaceTimeAttnPipeline(steps=50, with_vae=False, cuda_graphs=False, half_weights=True, use_checkpoint=False)
 unet = pipe.model.model.diffusion_model
 unet.set_checkpointing(False)
+if len(sys.argv) > 1 and sys.argv[1] == "cl":
+    unet.to(memory_format=torch.channels_last)
 items = P.build_work_items(P.read_gpt(P.SYNTHETIC_GPT))[:1]
 cond = pipe.to_device(pipe.encode(items))
 unet.set_local_contexts([cond["locals"][i] for i in range(2)], first_timestep=981)
@@ -29,4 +31,4 @@ for bwd in (False, True):
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         run(bwd); torch.cuda.synchronize()
     print("==== backward" if bwd else "==== forward only")
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=70))
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))
