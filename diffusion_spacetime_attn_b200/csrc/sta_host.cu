@@ -75,6 +75,25 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return STA_OK;
 }
 
+int make_tmap_f32_dense(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(STA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(STA_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r);
+  return STA_OK;
+}
+
 }  // namespace sta
 
 extern "C" {

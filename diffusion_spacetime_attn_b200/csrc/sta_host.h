@@ -30,4 +30,8 @@ unsigned int* device_error_word();
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
 
+// Tiled fp32 tensor map WITHOUT swizzle (dense box rows), used as the destination of TMA reduce-add.
+int make_tmap_f32_dense(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box);
+
 }  // namespace sta

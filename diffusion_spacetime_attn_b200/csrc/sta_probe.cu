@@ -24,6 +24,8 @@ struct ProbeDev {
   unsigned char* smem_dump;
   int dump_bytes;
   unsigned int* err;
+  int reps;
+  long long* cycles;
 };
 
 constexpr int kProbeOperandBytes = 64 * 1024;
@@ -85,16 +87,35 @@ probe_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (tid == 0) {
     if (mbar_wait(&bar_tma, 0, &dead, p.err, 1)) {
       tc_fence_after();
-      for (int k = 0; k < p.nk; ++k) {
-        uint64_t bd = umma_desc(p.b_desc_hi, smem_u32(sB) + p.b_off[k]);
-        if (p.a_in_tmem) {
-          umma_ts(tmem, tmem + 256 + p.a_off[k], bd, p.idesc, k > 0);
-        } else {
-          uint64_t ad = umma_desc(p.a_desc_hi, smem_u32(sA) + p.a_off[k]);
-          umma_ss(tmem, ad, bd, p.idesc, k > 0);
+      // descriptors are built before the timed region so that the loop below is (predicated) MMA issue only
+      uint64_t adesc[16], bdesc[16];
+      uint32_t atm[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        bdesc[k] = umma_desc(p.b_desc_hi, smem_u32(sB) + p.b_off[k]);
+        adesc[k] = umma_desc(p.a_desc_hi, smem_u32(sA) + p.a_off[k]);
+        atm[k] = tmem + 256 + p.a_off[k];
+      }
+      const bool alt = p.dump_bytes == -1;
+      const int reps = p.reps > 1 ? p.reps : 1;
+      const int nk = p.nk;
+      const long long t0 = clock64();
+      for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (k < nk) {
+            const uint32_t d = tmem + (alt ? (k & 1) * 128 : 0);
+            const uint32_t acc = (k > (alt ? 1 : 0)) || rep > 0;
+            if (p.a_in_tmem) umma_ts(d, atm[k], bdesc[k], p.idesc, acc);
+            else umma_ss(d, adesc[k], bdesc[k], p.idesc, acc);
+          }
         }
       }
       umma_commit(&bar_mma);
+      if (p.cycles) {
+        mbar_wait(&bar_mma, 0, &dead, p.err, 3);
+        p.cycles[0] = clock64() - t0;
+      }
     }
   }
   __syncwarp();
@@ -157,9 +178,68 @@ extern "C" int sta_probe_gemm(const sta_probe_args* a, void* stream) {
   p.smem_dump = reinterpret_cast<unsigned char*>(a->smem_dump);
   p.dump_bytes = a->dump_bytes;
   p.err = device_error_word();
+  p.reps = a->reps;
+  p.cycles = reinterpret_cast<long long*>(a->cycles);
   const int smem_bytes = 2 * kProbeOperandBytes + 1024;
   STA_CUDA_CHECK(cudaFuncSetAttribute(probe_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   probe_gemm_kernel<<<1, 128, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(tm_a, tm_b, p);
+  STA_CUDA_CHECK(cudaGetLastError());
+  return STA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMEM load/store throughput probe: `warps` warps (multiple of 4) each read (or write) `iters` x 32 columns of
+// their 32 lanes; reports SM cycles for the whole CTA.  bytes = warps * 32 lanes * 32 cols * 4 B * iters.
+// ---------------------------------------------------------------------------------------------------------
+namespace sta {
+__global__ void __launch_bounds__(512, 1) tmem_bw_kernel(int iters, int mode, long long* cycles, unsigned int* sink) {
+  __shared__ uint32_t tmem_base_s;
+  __shared__ long long t_begin;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_base_s + ((uint32_t)((warp & 3) << 5) << 16) + (warp >> 2) * 64;
+  uint32_t acc = 0;
+  uint32_t r[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = threadIdx.x + i;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+      tmem_ld32(base + (it & 1) * 32, r);
+      tmem_ld_wait();
+      acc += r[0] ^ r[13] ^ r[31];
+    } else if (mode == 1) {  // two loads in flight
+      uint32_t r2[32];
+      tmem_ld32(base, r);
+      tmem_ld32(base + 32, r2);
+      tmem_ld_wait();
+      acc += r[0] ^ r[31] ^ r2[7] ^ r2[31];
+    } else {
+      tmem_st16(base + (it & 1) * 16, r);
+      tmem_st_wait();
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+  if (acc == 0xdeadbeef) sink[0] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+}  // namespace sta
+
+extern "C" int sta_probe_tmem_bw(int warps, int iters, int mode, long long* cycles_dev, void* stream) {
+  using namespace sta;
+  if (warps < 4 || warps > 16 || (warps % 4)) return fail(STA_ERR_BAD_ARG, "warps must be 4, 8, 12 or 16");
+  tmem_bw_kernel<<<1, warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(iters, mode, cycles_dev, device_error_word());
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }

@@ -14,6 +14,8 @@
 //   3. sattn_dq_cast_kernel   dq_accum fp32 -> d_q fp16
 #include "../../include/sta_b200.h"
 #include "sta_common.cuh"
+#include <stdlib.h>
+
 #include "sta_host.h"
 
 namespace sta {
@@ -25,7 +27,6 @@ struct SattnBwdCfg {
   static constexpr int DMMA = (D + 15) / 16 * 16;
   static constexpr int NBLK = (D + 63) / 64;
   static constexpr int TILE = NBLK * kSBBlockBytes;
-  static constexpr int ST = (NBLK == 3) ? 1 : 2;  // (Q_i, dO_i) ring depth
   // TMEM: S^T [0,128) dP^T [128,256) dV, dK, dQ accumulators of NACC columns each.  For D = 160 three 160-column
   // accumulators do not fit: the head dim is processed in NPASS = 2 column passes split at a 64-column smem
   // block boundary ([0,128) then [128,160)), S^T / dP^T are recomputed per pass, and the dQ accumulator shares
@@ -33,12 +34,23 @@ struct SattnBwdCfg {
   static constexpr int NPASS = (DMMA > 128) ? 2 : 1;
   static constexpr int NACC_MAX = (NPASS == 1) ? DMMA : 128;
   static constexpr bool ALIAS_DQ = NPASS > 1;
+  // MODE 2 (one smem block per tile, d <= 64): dS^T double-buffered, S^T/dP^T of the NEXT query tile are issued
+  //         half a tile ahead, so the tensor pipe and the two math warpgroups overlap.
+  // MODE 1 / 0: single dS^T buffer; the next tile's S^T/dP^T follow dQ (MODE 0 also waits for the dQ drain).
+  static constexpr int MODE = ALIAS_DQ ? 0 : (NBLK == 1 ? 2 : 1);
+  static constexpr int ST = (NBLK == 3) ? 1 : 2;            // (Q_i, dO_i) ring depth
+  static constexpr int NDS = (MODE == 2) ? 2 : 1;           // dS^T buffers
   static constexpr int TMEM_DV = 256;
   static constexpr int TMEM_DK = 256 + NACC_MAX;
   static constexpr int TMEM_DQ = ALIAS_DQ ? 0 : 256 + 2 * NACC_MAX;
+  // MODE 2 also double-buffers the dQ accumulator (256 + 4*48 = 448 columns) so that the math warps drain dQ of
+  // tile i-1 AFTER the P/dS math of tile i, off the critical path.
+  static constexpr bool PIPE_DRAIN = (MODE == 2) && (256 + 4 * NACC_MAX <= 512);
+  static constexpr int DQ_STRIDE = PIPE_DRAIN ? NACC_MAX : 0;
   static constexpr int DS_BYTES = 2 * kSBBlockBytes;  // dS^T: 128 keys x 128 queries fp16
-  static constexpr int SMEM_BYTES = 2 * TILE + 2 * ST * TILE + DS_BYTES + 1024;
-  static constexpr int THREADS = 192;
+  static constexpr int STAGE_BYTES = PIPE_DRAIN ? 128 * D * 4 : 0;  // fp32 dQ tile staged for the TMA reduce-add
+  static constexpr int SMEM_TOTAL = 2 * TILE + 2 * ST * TILE + NDS * DS_BYTES + STAGE_BYTES + 1024;
+  static constexpr int THREADS = 64 + 256;  // TMA warp, MMA warp, two math warpgroups
 };
 
 struct SattnBwdParams {
@@ -50,19 +62,27 @@ struct SattnBwdParams {
   int n, heads;
   float scale, scale_log2;
   unsigned int* err;
+  int dbg;
 };
+
+// cycle counters of CTA (0,0,0) when STA_DEBUG_FLAGS & 8: [0..4] math warp 2: wait sdp, compute, wait dq, drain, total;
+// [8..10] MMA thread: wait pds, issue, total
+__device__ long long g_bwd_dbg[16];
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Query tile i is processed as two halves of 64 query columns (h = 0, 1).  Math warpgroup h owns half h: one thread per
+// key row (TMEM lane), 64 columns of S^T and dP^T.
 template <int D>
 __global__ void __launch_bounds__(SattnBwdCfg<D>::THREADS, 1)
 sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                 const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dq1,
                  const SattnBwdParams p) {
   using Cfg = SattnBwdCfg<D>;
-  constexpr int ST = Cfg::ST, NBLK = Cfg::NBLK, DMMA = Cfg::DMMA;
+  constexpr int ST = Cfg::ST, NBLK = Cfg::NBLK, DMMA = Cfg::DMMA, MODE = Cfg::MODE;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem =
@@ -71,25 +91,26 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   unsigned char* sV = sK + Cfg::TILE;
   unsigned char* sQ = sV + Cfg::TILE;          // ring: stage s -> Q at sQ + s*2*TILE, dO right after it
   unsigned char* sDS = sQ + 2 * ST * Cfg::TILE;
+  float* sStage = reinterpret_cast<float*>(sDS + Cfg::NDS * Cfg::DS_BYTES);  // [128][D] fp32 (PIPE_DRAIN only)
 
-  __shared__ uint64_t kv_full, qdo_full[ST], qdo_empty[ST], sdp_full, pds_ready, dq_full, dq_drained;
+  __shared__ uint64_t kv_full, qdo_full[ST], qdo_empty[ST], sdp_full[2], pds_ready[2], dq_full, dq_drained;
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
-  __shared__ float s_lse2[128], s_delta[128];  // lse*log2e and delta of the current query tile
+  __shared__ __align__(16) float s_lse2[128], s_delta[128];  // lse*log2e and delta of the current query tile
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int n = p.n;
   const int T = (n + 127) / 128;
+  const int total = Cfg::NPASS * T;
 
   if (tid == 0) {
     dead = 0;
     mbar_init(&kv_full, 1);
     for (int i = 0; i < ST; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(&sdp_full, 1);
-    mbar_init(&pds_ready, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&pds_ready[i], 4); }
     mbar_init(&dq_full, 1);
-    mbar_init(&dq_drained, 4);
+    mbar_init(&dq_drained, 8);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -109,182 +130,306 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      mbar_expect_tx(&kv_full, 2 * Cfg::TILE);
+    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
+      mbar_expect_tx_w(&kv_full, 2 * Cfg::TILE);
       for (int blk = 0; blk < NBLK; ++blk) {
-        tma_load_4d(sK + blk * kSBBlockBytes, &tm_k, &kv_full, blk * 64, h, j * 128, b);
-        tma_load_4d(sV + blk * kSBBlockBytes, &tm_v, &kv_full, blk * 64, h, j * 128, b);
+        tma_load_4d_w(sK + blk * kSBBlockBytes, &tm_k, &kv_full, blk * 64, h, j * 128, b);
+        tma_load_4d_w(sV + blk * kSBBlockBytes, &tm_v, &kv_full, blk * 64, h, j * 128, b);
       }
-      for (int it = 0; it < Cfg::NPASS * T; ++it) {
+      for (int it = 0; it < total; ++it) {
         const int st = it % ST, i = it % T;
-        if (!mbar_wait(&qdo_empty[st], ((it / ST) & 1) ^ 1, &dead, p.err, 10)) break;
-        mbar_expect_tx(&qdo_full[st], 2 * Cfg::TILE);
+        if (!mbar_wait_warp(&qdo_empty[st], ((it / ST) & 1) ^ 1, &dead, p.err, 10)) break;
+        mbar_expect_tx_w(&qdo_full[st], 2 * Cfg::TILE);
         unsigned char* dq = sQ + st * 2 * Cfg::TILE;
         for (int blk = 0; blk < NBLK; ++blk) {
-          tma_load_4d(dq + blk * kSBBlockBytes, &tm_q, &qdo_full[st], blk * 64, h, i * 128, b);
-          tma_load_4d(dq + Cfg::TILE + blk * kSBBlockBytes, &tm_do, &qdo_full[st], blk * 64, h, i * 128, b);
+          tma_load_4d_w(dq + blk * kSBBlockBytes, &tm_q, &qdo_full[st], blk * 64, h, i * 128, b);
+          tma_load_4d_w(dq + Cfg::TILE + blk * kSBBlockBytes, &tm_do, &qdo_full[st], blk * 64, h, i * 128, b);
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
       constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);              // K-major, 128B swizzle
       constexpr uint64_t mndesc_hi = umma_desc_hi_sw128(kSBBlockBytes, 1024);  // MN-major, 128-row blocks
-      constexpr uint32_t idesc_nt = umma_idesc_f16(128, 128, 0, 0);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), ds_addr = smem_u32(sDS);
+      constexpr uint32_t idesc_half = umma_idesc_f16(128, 64, 0, 0);           // [128 keys x d] x [64 queries x d]^T
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
 
-      bool ok = mbar_wait(&kv_full, 0, &dead, p.err, 20);
-      for (int it = 0; it < Cfg::NPASS * T && ok; ++it) {
+      auto stage_addr = [&](int it) { return smem_u32(sQ + (it % ST) * 2 * Cfg::TILE); };
+      // S^T_half = K_j Q_half^T and dP^T_half = V_j dO_half^T; half hf covers query rows [64 hf, 64 hf + 64)
+      auto issue_sdp = [&](int it, int hf) {
+        const uint32_t q_addr = stage_addr(it) + hf * 8192, do_addr = q_addr + Cfg::TILE;
+#pragma unroll
+        for (int k = 0; k < DMMA / 16; ++k) {
+          const uint32_t off = (k / 4) * kSBBlockBytes + (k % 4) * 32;
+          umma_ss_w(tmem + hf * 64, umma_desc(kdesc_hi, k_addr + off), umma_desc(kdesc_hi, q_addr + off), idesc_half, k > 0);
+        }
+#pragma unroll
+        for (int k = 0; k < DMMA / 16; ++k) {
+          const uint32_t off = (k / 4) * kSBBlockBytes + (k % 4) * 32;
+          umma_ss_w(tmem + 128 + hf * 64, umma_desc(kdesc_hi, v_addr + off), umma_desc(kdesc_hi, do_addr + off), idesc_half,
+                  k > 0);
+        }
+        umma_commit_w(&sdp_full[hf]);
+      };
+
+      bool ok = mbar_wait_warp(&kv_full, 0, &dead, p.err, 20) && mbar_wait_warp(&qdo_full[0], 0, &dead, p.err, 21);
+      if (ok) {
+        tc_fence_after();
+        issue_sdp(0, 0);
+        issue_sdp(0, 1);
+      }
+      const bool prof = (p.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      long long m_wait = 0, m_wait_q = 0, m_all = clock64(), mt;
+      for (int it = 0; it < total && ok; ++it) {
         const int st = it % ST, pass = it / T, i = it % T;
         const int nacc = (Cfg::NPASS == 1) ? DMMA : (pass == 0 ? 128 : DMMA - 128);
         const uint32_t col_off = pass * 2 * kSBBlockBytes;               // first 64-column block of this pass
         const uint32_t idesc_acc = umma_idesc_f16(128, nacc, 0, 1);      // A K-major (TMEM or smem), B MN-major
         const uint32_t idesc_dq = umma_idesc_f16(128, nacc, 1, 1);       // A M-major (dS^T read transposed)
-        const uint32_t q_addr = smem_u32(sQ + st * 2 * Cfg::TILE), do_addr = q_addr + Cfg::TILE;
-        ok = mbar_wait(&qdo_full[st], (it / ST) & 1, &dead, p.err, 21);
-        if (ok && Cfg::ALIAS_DQ && it > 0) ok = mbar_wait(&dq_drained, (it - 1) & 1, &dead, p.err, 22);
-        if (!ok) break;
-        tc_fence_after();
+        const uint32_t q_addr = stage_addr(it), do_addr = q_addr + Cfg::TILE;
+        const uint32_t ds_addr = smem_u32(sDS + (it % Cfg::NDS) * Cfg::DS_BYTES);
+        const bool more = it + 1 < total;
+        for (int hf = 0; hf < 2 && ok; ++hf) {
+          mt = clock64();
+          ok = mbar_wait_warp(&pds_ready[hf], it & 1, &dead, p.err, 23 + hf);
+          m_wait += clock64() - mt;
+          if (!ok) break;
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < DMMA / 16; ++k) {
-          const uint32_t off = (k / 4) * kSBBlockBytes + (k % 4) * 32;
-          umma_ss(tmem, umma_desc(kdesc_hi, k_addr + off), umma_desc(kdesc_hi, q_addr + off), idesc_nt, k > 0);
+          for (int k = 0; k < 4; ++k)  // dV += P^T_half dO_half   (K = 64 queries of this half)
+            umma_ts_w(tmem + Cfg::TMEM_DV, tmem + hf * 64 + k * 8,
+                    umma_desc(mndesc_hi, do_addr + col_off + hf * 8192 + k * 2048), idesc_acc, i > 0 || hf > 0 || k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // dK += dS^T_half Q_half
+            umma_ss_w(tmem + Cfg::TMEM_DK, umma_desc(kdesc_hi, ds_addr + hf * kSBBlockBytes + k * 32),
+                    umma_desc(mndesc_hi, q_addr + col_off + hf * 8192 + k * 2048), idesc_acc, i > 0 || hf > 0 || k > 0);
+          if (hf == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)  // dQ_i = dS K_j   (M = 128 queries, K = 128 keys)
+              umma_ss_w(tmem + Cfg::TMEM_DQ + (it & 1) * Cfg::DQ_STRIDE, umma_desc(mndesc_hi, ds_addr + k * 2048),
+                      umma_desc(mndesc_hi, k_addr + col_off + k * 2048), idesc_dq, k > 0);
+            umma_commit_w(&dq_full);
+            umma_commit_w(&qdo_empty[st]);
+          }
+          if (more) {
+            if (MODE == 2) {
+              // next tile's half hf: its S^T/dP^T columns and P^T alias were consumed by the MMAs issued above
+              if (hf == 0) {
+                mt = clock64();
+                ok = mbar_wait_warp(&qdo_full[(it + 1) % ST], ((it + 1) / ST) & 1, &dead, p.err, 25);
+                m_wait_q += clock64() - mt;
+                if (!ok) break;
+                tc_fence_after();
+              }
+              issue_sdp(it + 1, hf);
+            } else if (hf == 1) {
+              ok = mbar_wait_warp(&qdo_full[(it + 1) % ST], ((it + 1) / ST) & 1, &dead, p.err, 25);
+              if (ok && MODE == 0) ok = mbar_wait_warp(&dq_drained, it & 1, &dead, p.err, 26);
+              if (!ok) break;
+              tc_fence_after();
+              issue_sdp(it + 1, 0);
+              issue_sdp(it + 1, 1);
+            }
+          }
         }
-#pragma unroll
-        for (int k = 0; k < DMMA / 16; ++k) {
-          const uint32_t off = (k / 4) * kSBBlockBytes + (k % 4) * 32;
-          umma_ss(tmem + 128, umma_desc(kdesc_hi, v_addr + off), umma_desc(kdesc_hi, do_addr + off), idesc_nt, k > 0);
-        }
-        umma_commit(&sdp_full);
-        ok = mbar_wait(&pds_ready, it & 1, &dead, p.err, 23);
-        if (!ok) break;
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // dV += P^T dO_i
-          umma_ts(tmem + Cfg::TMEM_DV, tmem + k * 8, umma_desc(mndesc_hi, do_addr + col_off + k * 2048), idesc_acc,
-                  i > 0 || k > 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // dK += dS^T Q_i
-          umma_ss(tmem + Cfg::TMEM_DK, umma_desc(kdesc_hi, ds_addr + (k / 4) * kSBBlockBytes + (k % 4) * 32),
-                  umma_desc(mndesc_hi, q_addr + col_off + k * 2048), idesc_acc, i > 0 || k > 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // dQ_i = dS K_j
-          umma_ss(tmem + Cfg::TMEM_DQ, umma_desc(mndesc_hi, ds_addr + k * 2048),
-                  umma_desc(mndesc_hi, k_addr + col_off + k * 2048), idesc_dq, k > 0);
-        umma_commit(&dq_full);
-        umma_commit(&qdo_empty[st]);
       }
+      if (prof) { g_bwd_dbg[8] = m_wait; g_bwd_dbg[9] = m_wait_q; g_bwd_dbg[10] = clock64() - m_all; }
     }
   } else {
     // ===================================== per-key-row math ==================================
-    const int r = ((warp & 3) << 5) + lane;  // row inside the tile: key row for S^T/dP^T, query row for dQ_i
-    const int t128 = tid - 64;               // 0..127 among the four math warps
+    const int g = (warp - 2) >> 2;           // math warpgroup = query half
+    const int r = ((warp & 3) << 5) + lane;  // key row for S^T/dP^T/dK/dV, query row for dQ_i
+    const int t128 = tid - 64 - g * 128;     // 0..127 inside the warpgroup
     const int key = j * 128 + r;
     const bool key_ok = key < n;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
     const float* lse_bh = p.lse + ((long long)b * p.heads + h) * n;
     const float* delta_bh = p.delta + ((long long)b * p.heads + h) * n;
+    auto drain_dq = [&](int it_d) {
+      const int q0row = (it_d % T) * 128, col0 = (it_d / T) * 128;
+      const int ncols = (Cfg::NPASS == 1) ? D : (it_d / T == 0 ? 128 : D - 128);
+      const uint32_t src = lane_addr + Cfg::TMEM_DQ + (it_d & 1) * Cfg::DQ_STRIDE;
+      if (Cfg::PIPE_DRAIN) {
+        // TMEM -> fp32 smem tile -> ONE TMA reduce-add per warpgroup and tile (the per-thread red.global path below
+        // costs ~1500 cycles per tile in LSU back-pressure; the bulk reduction is asynchronous).  Warpgroup 0 owns
+        // head-dim columns [0, 24), warpgroup 1 columns [24, D): no synchronisation between the warpgroups.
+        constexpr int W0 = 24, W1 = D - 24;
+        const int wcols = g == 0 ? W0 : W1, cbase = g == 0 ? 0 : W0;
+        float* stage = sStage + (g == 0 ? 0 : 128 * W0);
+        if (t128 == 0) bulk_wait_group_read0();  // this warpgroup's previous reduce has finished reading its tile
+        named_bar_sync(5 + g, 128);
+#pragma unroll
+        for (int c0 = 0; c0 < W0; c0 += 8) {
+          if (c0 >= wcols) break;
+          uint32_t o[8];
+          tmem_ld8(src + cbase + c0, o);
+          tmem_ld_wait();
+          float4* d4 = reinterpret_cast<float4*>(stage + r * wcols + c0);
+          d4[0] = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
+          d4[1] = make_float4(__uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]), __uint_as_float(o[7]));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(7 + g, 128);
+        if (t128 == 0 && !(p.dbg & 1)) {
+          tma_reduce_add_4d(g == 0 ? &tm_dq : &tm_dq1, stage, cbase, h, q0row, b);  // OOB rows are clipped by TMA
+          bulk_commit_group();
+        }
+        return;
+      }
+      const int qrow = q0row + r;
+      float* dst = p.dq_accum + ((long long)b * n + qrow) * (p.heads * D) + h * D + col0;
+#pragma unroll
+      for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 16) {
+        const int cc = c0 + 8 * g;
+        if (cc >= ncols) break;
+        uint32_t o[8];
+        tmem_ld8(src + cc, o);
+        tmem_ld_wait();
+        if (qrow < n && !(p.dbg & 1)) {
+          red_add_v4(dst + cc, __uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
+          red_add_v4(dst + cc + 4, __uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]), __uint_as_float(o[7]));
+        }
+      }
+    };
+    // per-thread prefetch of one staged statistic: threads 0..63 of a warpgroup own -lse*log2e, 64..127 own -delta*scale
+    auto load_stat = [&](int it_n) -> float {
+      if (it_n >= total) return 0.f;
+      const int qi = (it_n % T) * 128 + g * 64 + (t128 & 63);
+      if (t128 < 64) return qi < n ? -lse_bh[qi] * 1.4426950408889634f : -INFINITY;
+      return qi < n ? -delta_bh[qi] * p.scale : 0.f;
+    };
+    float pre_val = load_stat(0);
     bool ok = true;
-    for (int it = 0; it < Cfg::NPASS * T; ++it) {
+    const bool prof = (p.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+    long long c_wait_sdp = 0, c_comp = 0, c_wait_dq = 0, c_drain = 0, t_all = clock64(), tt;
+    for (int it = 0; it < total; ++it) {
       const int pass = it / T, i = it % T;
       const int col0 = pass * 128;                                             // first head-dim column of this pass
       const int ncols = (Cfg::NPASS == 1) ? D : (pass == 0 ? 128 : D - 128);   // columns of this pass
-      // stage lse/delta of this query tile for broadcast reads
+      // stage lse / delta of this warpgroup's 64 query columns for broadcast reads (values were prefetched from
+      // global memory one tile ahead, so the load latency is off the critical path)
       {
-        const int qi = i * 128 + t128;
-        s_lse2[t128] = qi < n ? lse_bh[qi] * 1.4426950408889634f : INFINITY;
-        s_delta[t128] = qi < n ? delta_bh[qi] : 0.f;
+        const int c = t128 & 63;
+        if (t128 < 64) s_lse2[g * 64 + c] = pre_val;
+        else s_delta[g * 64 + c] = pre_val;
       }
-      named_bar_sync(1, 128);
-      ok = mbar_wait_warp(&sdp_full, it & 1, &dead, p.err, 30);
+      named_bar_sync(1 + g, 128);
+      pre_val = load_stat(it + 1);
+      tt = clock64();
+      ok = mbar_wait_warp(&sdp_full[g], it & 1, &dead, p.err, 30);
       if (!ok) break;
       tc_fence_after();
-      const float* lse2 = s_lse2;
-      const float* dlt = s_delta;
+      c_wait_sdp += clock64() - tt; tt = clock64();
+      const float* lse2 = s_lse2 + g * 64;
+      const float* dlt = s_delta + g * 64;
+      unsigned char* ds_blk = sDS + (it % Cfg::NDS) * Cfg::DS_BYTES + g * kSBBlockBytes;
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t s[32], dp[32];
-        tmem_ld32(lane_addr + c0, s);
-        tmem_ld32(lane_addr + 128 + c0, dp);
+        tmem_ld32(lane_addr + g * 64 + c0, s);
+        tmem_ld32(lane_addr + 128 + g * 64 + c0, dp);
         tmem_ld_wait();
         uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int q = 0; q < 32; q += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(s[q]), p.scale_log2, -lse2[c0 + q]));
-          float p1 = fast_exp2(fmaf(__uint_as_float(s[q + 1]), p.scale_log2, -lse2[c0 + q + 1]));
-          if (!key_ok) { p0 = 0.f; p1 = 0.f; }
-          const float d0 = p.scale * p0 * (__uint_as_float(dp[q]) - dlt[c0 + q]);
-          const float d1 = p.scale * p1 * (__uint_as_float(dp[q + 1]) - dlt[c0 + q + 1]);
-          pk[q >> 1] = pack_half2(p0, p1);
-          dk[q >> 1] = pack_half2(d0, d1);
+        for (int q = 0; q < 32; q += 4) {
+          const float4 nl = *reinterpret_cast<const float4*>(lse2 + c0 + q);   // broadcast reads, 4 columns at a time
+          const float4 nd = *reinterpret_cast<const float4*>(dlt + c0 + q);
+          const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, ndv[4] = {nd.x, nd.y, nd.z, nd.w};
+          float pv[4], dv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = fmaf(__uint_as_float(s[q + e]), p.scale_log2, nlv[e]);
+            pv[e] = (p.dbg & 4) ? x : fast_exp2(x);
+            dv[e] = pv[e] * fmaf(__uint_as_float(dp[q + e]), p.scale, ndv[e]);  // scale * P * (dP - delta)
+          }
+          pk[q >> 1] = pack_half2(pv[0], pv[1]);
+          pk[(q >> 1) + 1] = pack_half2(pv[2], pv[3]);
+          dk[q >> 1] = pack_half2(dv[0], dv[1]);
+          dk[(q >> 1) + 1] = pack_half2(dv[2], dv[3]);
         }
-        tmem_st16(lane_addr + (c0 >> 1), pk);
-        // dS^T row r, query columns [c0, c0+32): four 16-byte chunks of block c0/64
-        unsigned char* blk = sDS + (c0 >> 6) * kSBBlockBytes;
-        const int chunk0 = (c0 & 63) >> 3;
+        if (!key_ok) {  // keys past the end of the sequence (last tile only): P = dS = 0
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { pk[e] = 0u; dk[e] = 0u; }
+        }
+        tmem_st16(lane_addr + g * 64 + (c0 >> 1), pk);
+        // dS^T row r, query columns [64 g + c0, +32): four 16-byte chunks of block g
+        const int chunk0 = c0 >> 3;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           uint4 v = make_uint4(dk[4 * cc], dk[4 * cc + 1], dk[4 * cc + 2], dk[4 * cc + 3]);
-          *reinterpret_cast<uint4*>(blk + sw128_offset(r, chunk0 + cc)) = v;
+          if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(ds_blk + sw128_offset(r, chunk0 + cc)) = v;
         }
       }
       tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
+      const int it_d = Cfg::PIPE_DRAIN ? it - 1 : it;
+      if (Cfg::PIPE_DRAIN && it_d >= 0) {
+        // Wait for dQ of the previous tile BEFORE releasing this tile to the MMA warp: a parity wait must never fall
+        // two phases behind, and completion #it of dq_full cannot happen before pds_ready(it).
+        ok = mbar_wait_warp(&dq_full, it_d & 1, &dead, p.err, 31);
+        if (!ok) break;
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pds_ready);
-      named_bar_sync(2, 128);  // everyone is done reading s_lse2 / s_delta before the next tile overwrites them
-      // ---- drain dQ_i into the fp32 accumulator ----
-      ok = mbar_wait_warp(&dq_full, it & 1, &dead, p.err, 31);
-      if (!ok) break;
-      tc_fence_after();
-      {
-        const int qrow = i * 128 + r;
-        float* dst = p.dq_accum + ((long long)b * n + qrow) * (p.heads * D) + h * D + col0;
-#pragma unroll
-        for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 8) {
-          if (c0 >= ncols) break;
-          uint32_t o[8];
-          tmem_ld8(lane_addr + Cfg::TMEM_DQ + c0, o);
-          tmem_ld_wait();
-          if (qrow < n) {
-            red_add_v4(dst + c0, __uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
-            red_add_v4(dst + c0 + 4, __uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]), __uint_as_float(o[7]));
-          }
+      if (lane == 0) mbar_arrive(&pds_ready[g]);
+      named_bar_sync(3 + g, 128);  // the warpgroup is done reading its lse / delta staging area
+      c_comp += clock64() - tt; tt = clock64();
+      // ---- drain dQ into the fp32 accumulator: the warpgroups take alternate 8-column chunks.  With PIPE_DRAIN the
+      //      tile drained here is the PREVIOUS one (its MMAs finished while this tile's P/dS math ran) ----
+      if (it_d >= 0) {
+        if (!Cfg::PIPE_DRAIN) {
+          ok = mbar_wait_warp(&dq_full, it_d & 1, &dead, p.err, 31);
+          if (!ok) break;
         }
+        tc_fence_after();
+        c_wait_dq += clock64() - tt; tt = clock64();
+        drain_dq(it_d);
+      }
+      if (Cfg::PIPE_DRAIN && it == total - 1) {  // last tile: nothing left to overlap with
+        ok = mbar_wait_warp(&dq_full, it & 1, &dead, p.err, 32);
+        if (!ok) break;
+        tc_fence_after();
+        drain_dq(it);
       }
       if (i == T - 1) {
-        // ---- end of a pass: dK, dV columns [col0, col0 + ncols) of this key row ----
+        // ---- end of a pass: dK, dV columns [col0, col0 + ncols) of this key row (dq_full => all MMAs completed) ----
         __half* dk_row = p.d_k + ((long long)b * n + key) * (p.heads * D) + h * D + col0;
         __half* dv_row = p.d_v + ((long long)b * n + key) * (p.heads * D) + h * D + col0;
 #pragma unroll
-        for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 8) {
-          if (c0 >= ncols) break;
+        for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 16) {
+          const int cc = c0 + 8 * g;
+          if (cc >= ncols) break;
           uint32_t a[8], c[8];
-        tmem_ld8(lane_addr + Cfg::TMEM_DK + c0, a);
-        tmem_ld8(lane_addr + Cfg::TMEM_DV + c0, c);
-        tmem_ld_wait();
-        if (key_ok) {
-          uint4 v;
-          v.x = pack_half2(__uint_as_float(a[0]), __uint_as_float(a[1]));
-          v.y = pack_half2(__uint_as_float(a[2]), __uint_as_float(a[3]));
-          v.z = pack_half2(__uint_as_float(a[4]), __uint_as_float(a[5]));
-          v.w = pack_half2(__uint_as_float(a[6]), __uint_as_float(a[7]));
-          *reinterpret_cast<uint4*>(dk_row + c0) = v;
-          v.x = pack_half2(__uint_as_float(c[0]), __uint_as_float(c[1]));
-          v.y = pack_half2(__uint_as_float(c[2]), __uint_as_float(c[3]));
-          v.z = pack_half2(__uint_as_float(c[4]), __uint_as_float(c[5]));
-          v.w = pack_half2(__uint_as_float(c[6]), __uint_as_float(c[7]));
-            *reinterpret_cast<uint4*>(dv_row + c0) = v;
+          tmem_ld8(lane_addr + Cfg::TMEM_DK + cc, a);
+          tmem_ld8(lane_addr + Cfg::TMEM_DV + cc, c);
+          tmem_ld_wait();
+          if (key_ok) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(a[0]), __uint_as_float(a[1]));
+            v.y = pack_half2(__uint_as_float(a[2]), __uint_as_float(a[3]));
+            v.z = pack_half2(__uint_as_float(a[4]), __uint_as_float(a[5]));
+            v.w = pack_half2(__uint_as_float(a[6]), __uint_as_float(a[7]));
+            *reinterpret_cast<uint4*>(dk_row + cc) = v;
+            v.x = pack_half2(__uint_as_float(c[0]), __uint_as_float(c[1]));
+            v.y = pack_half2(__uint_as_float(c[2]), __uint_as_float(c[3]));
+            v.z = pack_half2(__uint_as_float(c[4]), __uint_as_float(c[5]));
+            v.w = pack_half2(__uint_as_float(c[6]), __uint_as_float(c[7]));
+            *reinterpret_cast<uint4*>(dv_row + cc) = v;
           }
         }
       }
-      if (Cfg::ALIAS_DQ) {
+      c_drain += clock64() - tt;
+      if (MODE == 0) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dq_drained);
       }
+    }
+    if (Cfg::PIPE_DRAIN && t128 == 0) bulk_wait_group0();  // all reduce-adds have landed before the kernel ends
+    if (prof) {
+      g_bwd_dbg[0] = c_wait_sdp; g_bwd_dbg[1] = c_comp; g_bwd_dbg[2] = c_wait_dq; g_bwd_dbg[3] = c_drain;
+      g_bwd_dbg[4] = clock64() - t_all;
     }
   }
   tc_fence_before();
@@ -349,6 +494,13 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
 
   const long long C = (long long)a->heads * D;
   const long long total = (long long)a->batch * a->n * a->heads;
+  CUtensorMap tm_dq, tm_dq1;
+  {
+    const uint64_t st[4] = {4, (uint64_t)D * 4, (uint64_t)C * 4, (uint64_t)a->n * C * 4};
+    const uint32_t bx0[4] = {24, 1, 128, 1}, bx1[4] = {(uint32_t)(D > 24 ? D - 24 : 8), 1, 128, 1};
+    if ((rc = make_tmap_f32_dense(&tm_dq, a->dq_accum, 4, dims, st, bx0))) return rc;
+    if ((rc = make_tmap_f32_dense(&tm_dq1, a->dq_accum, 4, dims, st, bx1))) return rc;
+  }
   STA_CUDA_CHECK(cudaMemsetAsync(a->dq_accum, 0, sizeof(float) * a->batch * a->n * C, stream));
   sattn_delta_kernel<D><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
       reinterpret_cast<const __half*>(a->out), reinterpret_cast<const __half*>(a->d_out), a->delta, a->batch, a->n,
@@ -366,13 +518,14 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   p.scale = a->scale;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.err = device_error_word();
+  p.dbg = getenv("STA_DEBUG_FLAGS") ? atoi(getenv("STA_DEBUG_FLAGS")) : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    STA_CUDA_CHECK(cudaFuncSetAttribute(sattn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    STA_CUDA_CHECK(cudaFuncSetAttribute(sattn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
     attr_set = true;
   }
   dim3 grid((a->n + 127) / 128, a->heads, a->batch);
-  sattn_bwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, p);
+  sattn_bwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_TOTAL, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, tm_dq1, p);
   STA_CUDA_CHECK(cudaGetLastError());
 
   const long long n4 = (long long)a->batch * a->n * C / 4;
@@ -383,6 +536,11 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
 }
 
 }  // namespace sta
+
+extern "C" int sta_debug_read(long long* out, int n) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, sta::g_bwd_dbg, sizeof(long long) * (n < 16 ? n : 16)) == cudaSuccess ? 0 : 3;
+}
 
 extern "C" int sta_sattn_bwd(const sta_sattn_bwd_args* a, void* stream) {
   using namespace sta;

@@ -62,7 +62,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int q0 = blockIdx.x * (128 * NQ), h = blockIdx.y, b = blockIdx.z;
   const int n = p.n;
   const int T = (n + 127) / 128;                           // KV tiles
@@ -92,26 +92,26 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      mbar_expect_tx(&q_full, nq_active * Cfg::TILE_BYTES);
+    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
+      mbar_expect_tx_w(&q_full, nq_active * Cfg::TILE_BYTES);
       for (int r = 0; r < nq_active; ++r)
         for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d(sQ + (r * NBLK + blk) * kBlockBytes, &tm_q, &q_full, blk * 64, h, q0 + r * 128, b);
+          tma_load_4d_w(sQ + (r * NBLK + blk) * kBlockBytes, &tm_q, &q_full, blk * 64, h, q0 + r * 128, b);
       for (int j = 0; j < T; ++j) {
         const int ks = j % KS, vs = j % VS;
-        if (!mbar_wait(&k_empty[ks], ((j / KS) & 1) ^ 1, &dead, p.err, 10)) break;
-        mbar_expect_tx(&k_full[ks], Cfg::TILE_BYTES);
+        if (!mbar_wait_warp(&k_empty[ks], ((j / KS) & 1) ^ 1, &dead, p.err, 10)) break;
+        mbar_expect_tx_w(&k_full[ks], Cfg::TILE_BYTES);
         for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d(sK + (ks * NBLK + blk) * kBlockBytes, &tm_k, &k_full[ks], blk * 64, h, j * 128, b);
-        if (!mbar_wait(&v_empty[vs], ((j / VS) & 1) ^ 1, &dead, p.err, 11)) break;
-        mbar_expect_tx(&v_full[vs], Cfg::TILE_BYTES);
+          tma_load_4d_w(sK + (ks * NBLK + blk) * kBlockBytes, &tm_k, &k_full[ks], blk * 64, h, j * 128, b);
+        if (!mbar_wait_warp(&v_empty[vs], ((j / VS) & 1) ^ 1, &dead, p.err, 11)) break;
+        mbar_expect_tx_w(&v_full[vs], Cfg::TILE_BYTES);
         for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d(sV + (vs * NBLK + blk) * kBlockBytes, &tm_v, &v_full[vs], blk * 64, h, j * 128, b);
+          tma_load_4d_w(sV + (vs * NBLK + blk) * kBlockBytes, &tm_v, &v_full[vs], blk * 64, h, j * 128, b);
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
       constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);            // K-major operands
       constexpr uint64_t vdesc_hi = umma_desc_hi_sw128(kBlockBytes, 1024);   // MN-major V: LBO = block stride
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
@@ -122,42 +122,42 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
         for (int k = 0; k < DMMA / 16; ++k) {
           const uint32_t off = (k / 4) * kBlockBytes + (k % 4) * 32;
-          umma_ss(tmem + r * 128, umma_desc(kdesc_hi, q_addr + r * Cfg::TILE_BYTES + off),
+          umma_ss_w(tmem + r * 128, umma_desc(kdesc_hi, q_addr + r * Cfg::TILE_BYTES + off),
                   umma_desc(kdesc_hi, k_addr + ks * Cfg::TILE_BYTES + off), idesc_qk, k > 0);
         }
-        umma_commit(&s_full[r]);
+        umma_commit_w(&s_full[r]);
       };
       auto issue_pv = [&](int r, int vs, bool acc) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ts(tmem + Cfg::TMEM_O + r * DMMA, tmem + r * 128 + k * 8,
+          umma_ts_w(tmem + Cfg::TMEM_O + r * DMMA, tmem + r * 128 + k * 8,
                   umma_desc(vdesc_hi, v_addr + vs * Cfg::TILE_BYTES + k * 2048), idesc_pv, acc || k > 0);
       };
 
-      bool ok = mbar_wait(&q_full, 0, &dead, p.err, 20) && mbar_wait(&k_full[0], 0, &dead, p.err, 21);
+      bool ok = mbar_wait_warp(&q_full, 0, &dead, p.err, 20) && mbar_wait_warp(&k_full[0], 0, &dead, p.err, 21);
       if (ok) {
         tc_fence_after();
         for (int r = 0; r < nq_active; ++r) issue_qk(r, 0);
-        umma_commit(&k_empty[0]);
+        umma_commit_w(&k_empty[0]);
         for (int j = 0; j < T && ok; ++j) {
           const int vs = j % VS, ks1 = (j + 1) % KS;
           for (int r = 0; r < nq_active; ++r) {
-            ok = mbar_wait(&p_ready[r], j & 1, &dead, p.err, 22);
-            if (ok && r == 0) ok = mbar_wait(&v_full[vs], (j / VS) & 1, &dead, p.err, 23);
+            ok = mbar_wait_warp(&p_ready[r], j & 1, &dead, p.err, 22);
+            if (ok && r == 0) ok = mbar_wait_warp(&v_full[vs], (j / VS) & 1, &dead, p.err, 23);
             if (!ok) break;
             tc_fence_after();
             issue_pv(r, vs, j > 0);
-            if (r == nq_active - 1) umma_commit(&v_empty[vs]);
+            if (r == nq_active - 1) umma_commit_w(&v_empty[vs]);
             if (j + 1 < T) {
               if (r == 0) {
-                ok = mbar_wait(&k_full[ks1], ((j + 1) / KS) & 1, &dead, p.err, 24);
+                ok = mbar_wait_warp(&k_full[ks1], ((j + 1) / KS) & 1, &dead, p.err, 24);
                 if (!ok) break;
                 tc_fence_after();
               }
               issue_qk(r, ks1);
-              if (r == nq_active - 1) umma_commit(&k_empty[ks1]);
+              if (r == nq_active - 1) umma_commit_w(&k_empty[ks1]);
             } else {
-              umma_commit(&o_full[r]);
+              umma_commit_w(&o_full[r]);
             }
           }
         }

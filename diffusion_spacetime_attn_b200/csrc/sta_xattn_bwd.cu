@@ -73,7 +73,7 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ int n_tiles_s;
   __shared__ float dcoef_s[kBMaxObj];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, pr = blockIdx.z;
   const int n = p.n, B = p.prompts, n_obj = p.n_obj, n_slots = 2 + p.n_obj;
 
@@ -128,36 +128,36 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      mbar_expect_tx(&in_full, 3 * Cfg::QTILE);
+    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
+      mbar_expect_tx_w(&in_full, 3 * Cfg::QTILE);
       for (int blk = 0; blk < NBLK; ++blk) {
-        tma_load_4d(sQ + blk * kBQBlockBytes, &tm_q, &in_full, blk * 64, h, q0, pr);
-        tma_load_4d(sDOu + blk * kBQBlockBytes, &tm_do, &in_full, blk * 64, h, q0, pr);
-        tma_load_4d(sDOc + blk * kBQBlockBytes, &tm_do, &in_full, blk * 64, h, q0, pr + B);
+        tma_load_4d_w(sQ + blk * kBQBlockBytes, &tm_q, &in_full, blk * 64, h, q0, pr);
+        tma_load_4d_w(sDOu + blk * kBQBlockBytes, &tm_do, &in_full, blk * 64, h, q0, pr);
+        tma_load_4d_w(sDOc + blk * kBQBlockBytes, &tm_do, &in_full, blk * 64, h, q0, pr + B);
       }
       bool ok = true;
       for (int t = 0; t < T && ok; ++t) {
         const int st = t % ST, slot = pr * n_slots + tile_slot[t];
-        ok = mbar_wait(&kv_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 10);
+        ok = mbar_wait_warp(&kv_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 10);
         if (!ok) break;
-        mbar_expect_tx(&kv_full[st], 2 * Cfg::CTILE);
+        mbar_expect_tx_w(&kv_full[st], 2 * Cfg::CTILE);
         for (int blk = 0; blk < NBLK; ++blk) {
-          tma_load_4d(sK + (st * NBLK + blk) * kBCBlockBytes, &tm_k, &kv_full[st], blk * 64, h, 0, slot);
-          tma_load_4d(sV + (st * NBLK + blk) * kBCBlockBytes, &tm_v, &kv_full[st], blk * 64, h, 0, slot);
+          tma_load_4d_w(sK + (st * NBLK + blk) * kBCBlockBytes, &tm_k, &kv_full[st], blk * 64, h, 0, slot);
+          tma_load_4d_w(sV + (st * NBLK + blk) * kBCBlockBytes, &tm_v, &kv_full[st], blk * 64, h, 0, slot);
         }
         if (t == 0) {
           // re-fill the Q buffer with the conditional row once S_u = Q_u K_0^T has been computed
-          ok = mbar_wait(&qu_done, 0, &dead, p.err, 12);
+          ok = mbar_wait_warp(&qu_done, 0, &dead, p.err, 12);
           if (!ok) break;
-          mbar_expect_tx(&q2_full, Cfg::QTILE);
+          mbar_expect_tx_w(&q2_full, Cfg::QTILE);
           for (int blk = 0; blk < NBLK; ++blk)
-            tma_load_4d(sQ + blk * kBQBlockBytes, &tm_q, &q2_full, blk * 64, h, q0, pr + B);
+            tma_load_4d_w(sQ + blk * kBQBlockBytes, &tm_q, &q2_full, blk * 64, h, q0, pr + B);
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
       constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);
       constexpr uint64_t mndesc_hi = umma_desc_hi_sw128(kBCBlockBytes, 1024);
       constexpr uint32_t idesc_s = umma_idesc_f16(128, 80, 0, 0);      // [128 x D] x [80 x D]^T
@@ -171,7 +171,7 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int k = 0; k < DMMA / 16; ++k) {
           const uint32_t aoff = (k / 4) * kBQBlockBytes + (k % 4) * 32;
           const uint32_t boff = (k / 4) * kBCBlockBytes + (k % 4) * 32;
-          umma_ss(tmem + slot * 80, umma_desc(kdesc_hi, a_addr + aoff), umma_desc(kdesc_hi, b_addr + boff), idesc_s,
+          umma_ss_w(tmem + slot * 80, umma_desc(kdesc_hi, a_addr + aoff), umma_desc(kdesc_hi, b_addr + boff), idesc_s,
                   k > 0);
         }
       };
@@ -179,32 +179,32 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       auto issue_dq = [&](int slot, uint32_t kk_addr, bool acc) {
 #pragma unroll
         for (int k = 0; k < 5; ++k)
-          umma_ts(tmem + Cfg::TMEM_DQ, tmem + slot * 80 + k * 8, umma_desc(mndesc_hi, kk_addr + k * 2048), idesc_dq,
+          umma_ts_w(tmem + Cfg::TMEM_DQ, tmem + slot * 80 + k * 8, umma_desc(mndesc_hi, kk_addr + k * 2048), idesc_dq,
                   acc || k > 0);
       };
       auto issue_sdp = [&](int t) {  // conditional-row tile t >= 1 into pair (t & 1)
         const int st = t % ST, s_slot = (t & 1) * 2;
         issue_nt(s_slot, q_addr, k_addr + st * Cfg::CTILE);
         issue_nt(s_slot + 1, doc_addr, v_addr + st * Cfg::CTILE);
-        umma_commit(&sdp_full[t & 1]);
+        umma_commit_w(&sdp_full[t & 1]);
       };
 
-      bool ok = mbar_wait(&in_full, 0, &dead, p.err, 20) && mbar_wait(&kv_full[0], 0, &dead, p.err, 21);
+      bool ok = mbar_wait_warp(&in_full, 0, &dead, p.err, 20) && mbar_wait_warp(&kv_full[0], 0, &dead, p.err, 21);
       if (ok) {
         tc_fence_after();
         issue_nt(0, q_addr, k_addr);
-        umma_commit(&qu_done);
+        umma_commit_w(&qu_done);
         issue_nt(1, dou_addr, v_addr);
         issue_nt(2, doc_addr, v_addr);
-        umma_commit(&sdp_full[0]);
-        ok = mbar_wait(&ds_ready, 0, &dead, p.err, 22);
+        umma_commit_w(&sdp_full[0]);
+        ok = mbar_wait_warp(&ds_ready, 0, &dead, p.err, 22);
       }
       if (ok) {
         tc_fence_after();
         issue_dq(0, k_addr, false);
-        umma_commit(&dq_full);
-        umma_commit(&kv_empty[0]);
-        ok = mbar_wait(&q2_full, 0, &dead, p.err, 23) && mbar_wait(&kv_full[1 % ST], (1 / ST) & 1, &dead, p.err, 24);
+        umma_commit_w(&dq_full);
+        umma_commit_w(&kv_empty[0]);
+        ok = mbar_wait_warp(&q2_full, 0, &dead, p.err, 23) && mbar_wait_warp(&kv_full[1 % ST], (1 / ST) & 1, &dead, p.err, 24);
       }
       if (ok) {
         tc_fence_after();
@@ -213,20 +213,20 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       for (int t = 1; t < T && ok; ++t) {
         const int st = t % ST;
         if (Cfg::PREFETCH && t + 1 < T) {
-          ok = mbar_wait(&kv_full[(t + 1) % ST], ((t + 1) / ST) & 1, &dead, p.err, 25);
+          ok = mbar_wait_warp(&kv_full[(t + 1) % ST], ((t + 1) / ST) & 1, &dead, p.err, 25);
           if (!ok) break;
           tc_fence_after();
           issue_sdp(t + 1);
         }
-        ok = mbar_wait(&ds_ready, t & 1, &dead, p.err, 26);
-        if (ok && t == 1) ok = mbar_wait(&dq_drained, 0, &dead, p.err, 27);
+        ok = mbar_wait_warp(&ds_ready, t & 1, &dead, p.err, 26);
+        if (ok && t == 1) ok = mbar_wait_warp(&dq_drained, 0, &dead, p.err, 27);
         if (!ok) break;
         tc_fence_after();
         issue_dq((t & 1) * 2, k_addr + st * Cfg::CTILE, t > 1);
-        if (t == T - 1) umma_commit(&dq_full);
-        umma_commit(&kv_empty[st]);
+        if (t == T - 1) umma_commit_w(&dq_full);
+        umma_commit_w(&kv_empty[st]);
         if (!Cfg::PREFETCH && t + 1 < T) {
-          ok = mbar_wait(&kv_full[(t + 1) % ST], ((t + 1) / ST) & 1, &dead, p.err, 28);
+          ok = mbar_wait_warp(&kv_full[(t + 1) % ST], ((t + 1) / ST) & 1, &dead, p.err, 28);
           if (!ok) break;
           tc_fence_after();
           issue_sdp(t + 1);

@@ -71,7 +71,7 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ int tile_slot[2 + kXMaxObj];  // context slot of the t-th tile this CTA processes
   __shared__ int n_tiles_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, pr = blockIdx.z;
   const int n = p.n, B = p.prompts, n_obj = p.n_obj, n_slots = 2 + p.n_obj;
 
@@ -121,26 +121,26 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      mbar_expect_tx(&q_full, 2 * Cfg::QTILE);
+    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
+      mbar_expect_tx_w(&q_full, 2 * Cfg::QTILE);
       for (int r = 0; r < 2; ++r)
         for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d(sQ + (r * NBLK + blk) * kXQBlockBytes, &tm_q, &q_full, blk * 64, h, q0, pr + r * B);
+          tma_load_4d_w(sQ + (r * NBLK + blk) * kXQBlockBytes, &tm_q, &q_full, blk * 64, h, q0, pr + r * B);
       for (int t = 0; t < T; ++t) {
         const int st = t % ST, slot = pr * n_slots + tile_slot[t];
-        if (!mbar_wait(&k_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 10)) break;
-        mbar_expect_tx(&k_full[st], Cfg::CTILE);
+        if (!mbar_wait_warp(&k_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 10)) break;
+        mbar_expect_tx_w(&k_full[st], Cfg::CTILE);
         for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d(sK + (st * NBLK + blk) * kXCBlockBytes, &tm_k, &k_full[st], blk * 64, h, 0, slot);
-        if (!mbar_wait(&v_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 11)) break;
-        mbar_expect_tx(&v_full[st], Cfg::CTILE);
+          tma_load_4d_w(sK + (st * NBLK + blk) * kXCBlockBytes, &tm_k, &k_full[st], blk * 64, h, 0, slot);
+        if (!mbar_wait_warp(&v_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 11)) break;
+        mbar_expect_tx_w(&v_full[st], Cfg::CTILE);
         for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d(sV + (st * NBLK + blk) * kXCBlockBytes, &tm_v, &v_full[st], blk * 64, h, 0, slot);
+          tma_load_4d_w(sV + (st * NBLK + blk) * kXCBlockBytes, &tm_v, &v_full[st], blk * 64, h, 0, slot);
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
       constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);
       constexpr uint64_t vdesc_hi = umma_desc_hi_sw128(kXCBlockBytes, 1024);
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 80, 0, 0);
@@ -152,51 +152,51 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int k = 0; k < DMMA / 16; ++k) {
           const uint32_t qoff = (k / 4) * kXQBlockBytes + (k % 4) * 32;
           const uint32_t koff = (k / 4) * kXCBlockBytes + (k % 4) * 32;
-          umma_ss(tmem + r * Cfg::TMEM_S, umma_desc(kdesc_hi, q_addr + r * Cfg::QTILE + qoff),
+          umma_ss_w(tmem + r * Cfg::TMEM_S, umma_desc(kdesc_hi, q_addr + r * Cfg::QTILE + qoff),
                   umma_desc(kdesc_hi, k_addr + st * Cfg::CTILE + koff), idesc_qk, k > 0);
         }
-        umma_commit(&s_full[r]);
-        umma_commit(&k_empty[st]);
+        umma_commit_w(&s_full[r]);
+        umma_commit_w(&k_empty[st]);
       };
       auto issue_pv = [&](int r, int st, bool acc) {
 #pragma unroll
         for (int k = 0; k < 5; ++k)
-          umma_ts(tmem + Cfg::TMEM_O + r * DMMA, tmem + r * Cfg::TMEM_S + k * 8,
+          umma_ts_w(tmem + Cfg::TMEM_O + r * DMMA, tmem + r * Cfg::TMEM_S + k * 8,
                   umma_desc(vdesc_hi, v_addr + st * Cfg::CTILE + k * 2048), idesc_pv, acc || k > 0);
-        umma_commit(&v_empty[st]);
+        umma_commit_w(&v_empty[st]);
       };
 
-      bool ok = mbar_wait(&q_full, 0, &dead, p.err, 20) && mbar_wait(&k_full[0], 0, &dead, p.err, 21);
+      bool ok = mbar_wait_warp(&q_full, 0, &dead, p.err, 20) && mbar_wait_warp(&k_full[0], 0, &dead, p.err, 21);
       if (ok) {
         tc_fence_after();
         issue_qk(0, 0);
-        ok = mbar_wait(&k_full[1 % ST], (1 / ST) & 1, &dead, p.err, 22);
+        ok = mbar_wait_warp(&k_full[1 % ST], (1 / ST) & 1, &dead, p.err, 22);
       }
       if (ok) {
         tc_fence_after();
         issue_qk(1, 1 % ST);
-        ok = mbar_wait(&p_ready[0], 0, &dead, p.err, 23) && mbar_wait(&v_full[0], 0, &dead, p.err, 24);
+        ok = mbar_wait_warp(&p_ready[0], 0, &dead, p.err, 23) && mbar_wait_warp(&v_full[0], 0, &dead, p.err, 24);
       }
       if (ok) {
         tc_fence_after();
         issue_pv(0, 0, false);
-        umma_commit(&o_full[0]);
+        umma_commit_w(&o_full[0]);
       }
       for (int t = 1; t < T && ok; ++t) {
         const int st = t % ST;
-        ok = mbar_wait(&p_ready[1], (t - 1) & 1, &dead, p.err, 25) &&
-             mbar_wait(&v_full[st], (t / ST) & 1, &dead, p.err, 26);
+        ok = mbar_wait_warp(&p_ready[1], (t - 1) & 1, &dead, p.err, 25) &&
+             mbar_wait_warp(&v_full[st], (t / ST) & 1, &dead, p.err, 26);
         if (!ok) break;
         tc_fence_after();
         issue_pv(1, st, t > 1);
         if (t + 1 < T) {
           const int st1 = (t + 1) % ST;
-          ok = mbar_wait(&k_full[st1], ((t + 1) / ST) & 1, &dead, p.err, 27);
+          ok = mbar_wait_warp(&k_full[st1], ((t + 1) / ST) & 1, &dead, p.err, 27);
           if (!ok) break;
           tc_fence_after();
           issue_qk(1, st1);
         } else {
-          umma_commit(&o_full[1]);
+          umma_commit_w(&o_full[1]);
         }
       }
     }

@@ -21,6 +21,8 @@ EXPORTED_SYMBOLS = (
     "sta_xattn_fwd",
     "sta_xattn_bwd",
     "sta_probe_gemm",
+    "sta_probe_tmem_bw",
+    "sta_debug_read",
 )
 
 
@@ -83,7 +85,7 @@ class ProbeArgs(C.Structure):
         ("a_desc_hi", C.c_uint64), ("b_desc_hi", C.c_uint64),
         ("nk", C.c_int32), ("a_off", C.c_uint32 * 16), ("b_off", C.c_uint32 * 16),
         ("idesc", C.c_uint32), ("n", C.c_int32), ("out", C.c_void_p), ("smem_dump", C.c_void_p),
-        ("dump_bytes", C.c_int32),
+        ("dump_bytes", C.c_int32), ("reps", C.c_int32), ("cycles", C.c_void_p),
     ]
 
 

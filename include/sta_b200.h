@@ -159,9 +159,18 @@ typedef struct {
   float* out;         /* fp32 [128, n] */
   void* smem_dump;    /* optional: raw image of the staging shared memory */
   int32_t dump_bytes;
+  int32_t reps;       /* >1: issue the nk-step MMA group `reps` times back to back (timing) */
+  int64_t* cycles;    /* optional: SM cycles from first issue to completion of the last MMA */
 } sta_probe_args;
 
 int sta_probe_gemm(const sta_probe_args* args, void* stream);
+
+/* Test hook: TMEM load (mode 0: one x32 load in flight, 1: two) / store (mode 2: x16) throughput of one CTA with
+ * `warps` warps; *cycles_dev (device int64) receives the SM cycles for `iters` iterations. */
+int sta_probe_tmem_bw(int warps, int iters, int mode, long long* cycles_dev, void* stream);
+
+/* Debug hook: cycle counters written by sta_sattn_bwd when STA_DEBUG_FLAGS & 8 (tools/ only). Synchronises. */
+int sta_debug_read(long long* out, int n);
 
 #ifdef __cplusplus
 }
