@@ -75,6 +75,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// non-blocking probe (try_wait may suspend the thread for a system-defined time before answering "not yet")
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait.  `dead` is a CTA-shared flag: once any wait in the CTA timed out every later wait returns
 // immediately so that the CTA drains to its teardown in microseconds instead of seconds.
 #ifndef STA_WAIT_TIMEOUT_CYCLES

@@ -31,7 +31,14 @@ struct SattnCfg {
   static constexpr int TILE_BYTES = NBLK * kBlockBytes;
   static constexpr int SMEM_BYTES = (NQ + KS + VS) * TILE_BYTES + 1024;
   static constexpr int THREADS = 64 + 128 * NQ;
-  static constexpr int TMEM_O = 256;
+  // TMEM columns: S_r at 128 r.  When they fit, the packed-fp16 P_r tiles get their OWN 64 columns (SEP_P) instead
+  // of aliasing S_r: the next S_r = Q_r K_{j+1}^T can then be issued as soon as the softmax warps have READ S_r,
+  // i.e. it overlaps the exp phase instead of following the P V MMAs.  d=40: 256 + 128 + 96 = 480, d=160: 128 + 64 +
+  // 160 = 352 columns; d=80 (256 + 128 + 160 = 544) keeps the aliasing.
+  static constexpr bool SEP_P = (128 * NQ + 64 * NQ + NQ * DMMA) <= 512;
+  static constexpr int TMEM_P = SEP_P ? 128 * NQ : 0;
+  static constexpr int P_STRIDE = SEP_P ? 64 : 128;
+  static constexpr int TMEM_O = 128 * NQ + (SEP_P ? 64 * NQ : 0);
 };
 
 struct SattnFwdParams {
@@ -58,7 +65,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   unsigned char* sV = sK + KS * Cfg::TILE_BYTES;
 
   __shared__ uint64_t q_full, k_full[KS], k_empty[KS], v_full[VS], v_empty[VS];
-  __shared__ uint64_t s_full[NQ], p_ready[NQ], o_full[NQ];
+  __shared__ uint64_t s_full[NQ], s_consumed[NQ], p_ready[NQ], pv_done[NQ];
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
 
@@ -73,7 +80,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     mbar_init(&q_full, 1);
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < NQ; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
+    for (int i = 0; i < NQ; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_consumed[i], 4); mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -111,7 +120,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
+    // ONE issue warp serves both query tiles (measured: a second issue warp makes the kernel ~10 % slower).  Whole
+    // warp, warp-uniform control flow; the single-lane instructions are elected inside the *_w helpers.
+    {
       constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);            // K-major operands
       constexpr uint64_t vdesc_hi = umma_desc_hi_sw128(kBlockBytes, 1024);   // MN-major V: LBO = block stride
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
@@ -130,35 +141,62 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       auto issue_pv = [&](int r, int vs, bool acc) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ts_w(tmem + Cfg::TMEM_O + r * DMMA, tmem + r * 128 + k * 8,
+          umma_ts_w(tmem + Cfg::TMEM_O + r * DMMA, tmem + Cfg::TMEM_P + r * Cfg::P_STRIDE + k * 8,
                   umma_desc(vdesc_hi, v_addr + vs * Cfg::TILE_BYTES + k * 2048), idesc_pv, acc || k > 0);
+        umma_commit_w(&pv_done[r]);
       };
+      // warp-uniform "has this phase completed?" (try_wait: a negative answer suspends the warp for a while, which
+      // keeps this polling loop off the issue slots of the softmax warp sharing the scheduler)
+      auto ready = [&](uint64_t* bar, uint32_t parity) { return __all_sync(0xffffffffu, mbar_try_wait(bar, parity)); };
 
       bool ok = mbar_wait_warp(&q_full, 0, &dead, p.err, 20) && mbar_wait_warp(&k_full[0], 0, &dead, p.err, 21);
       if (ok) {
         tc_fence_after();
+        // Event-driven issue: each query tile r alternates  S_r(j+1) = Q_r K_{j+1}^T  (allowed once the softmax warps
+        // have read S_r(j) [SEP_P] / once P_r(j) V_j has been issued [aliased P])  and  O_r += P_r(j) V_j  (once
+        // P_r(j) is in TMEM).  Whichever tile has its next operand ready is served first.
+        int qk_next[2] = {1, 1}, pv_next[2] = {0, 0};
+        int k_rel = 0, v_rel = 0;  // K / V tiles released back to the TMA producer so far
         for (int r = 0; r < nq_active; ++r) issue_qk(r, 0);
-        umma_commit_w(&k_empty[0]);
-        for (int j = 0; j < T && ok; ++j) {
-          const int vs = j % VS, ks1 = (j + 1) % KS;
-          for (int r = 0; r < nq_active; ++r) {
-            ok = mbar_wait_warp(&p_ready[r], j & 1, &dead, p.err, 22);
-            if (ok && r == 0) ok = mbar_wait_warp(&v_full[vs], (j / VS) & 1, &dead, p.err, 23);
-            if (!ok) break;
-            tc_fence_after();
-            issue_pv(r, vs, j > 0);
-            if (r == nq_active - 1) umma_commit_w(&v_empty[vs]);
-            if (j + 1 < T) {
-              if (r == 0) {
-                ok = mbar_wait_warp(&k_full[ks1], ((j + 1) / KS) & 1, &dead, p.err, 24);
-                if (!ok) break;
+        if (nq_active == 1) { qk_next[1] = T; pv_next[1] = T; }
+        long long idle = 0;
+        while (pv_next[0] < T || pv_next[1] < T) {
+          bool progress = false;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (r >= nq_active) continue;
+            // service order matters because a failed try_wait suspends the warp for a while: with separate P
+            // buffers the latency-critical event is "S_r read" (-> next S_r), with aliased P it is "P_r ready"
+            auto try_qk = [&]() {
+              const int jq = qk_next[r];
+              if (jq < T && (Cfg::SEP_P ? ready(&s_consumed[r], (jq - 1) & 1) : (pv_next[r] >= jq)) &&
+                  ready(&k_full[jq % KS], (jq / KS) & 1)) {
                 tc_fence_after();
+                issue_qk(r, jq % KS);
+                qk_next[r] = jq + 1;
+                progress = true;
               }
-              issue_qk(r, ks1);
-              if (r == nq_active - 1) umma_commit_w(&k_empty[ks1]);
-            } else {
-              umma_commit_w(&o_full[r]);
-            }
+            };
+            auto try_pv = [&]() {
+              const int jp = pv_next[r];
+              if (jp < T && ready(&p_ready[r], jp & 1) && ready(&v_full[jp % VS], (jp / VS) & 1)) {
+                tc_fence_after();
+                issue_pv(r, jp % VS, jp > 0);
+                pv_next[r] = jp + 1;
+                progress = true;
+              }
+            };
+            if (Cfg::SEP_P) { try_qk(); try_pv(); } else { try_pv(); try_qk(); }
+          }
+          // a K (V) tile goes back to the producer once every active query tile has issued its MMA on it
+          const int k_done = min(qk_next[0], qk_next[1]), v_done = min(pv_next[0], pv_next[1]);
+          while (k_rel < min(k_done, T)) { umma_commit_w(&k_empty[k_rel % KS]); ++k_rel; }
+          while (v_rel < min(v_done, T)) { umma_commit_w(&v_empty[v_rel % VS]); ++v_rel; }
+          if (progress) {
+            idle = 0;
+          } else if (++idle > (1ll << 22) || dead) {  // seconds of polling without progress: give up loudly
+            if (!dead) { dead = 1; atomicCAS(p.err, 0u, STA_ERR_MBAR_TIMEOUT | 22u); }
+            break;
           }
         }
       }
@@ -171,6 +209,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const int row = q0 + r * 128 + row_in_tile;
       const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
       const uint32_t s_addr = lane_addr + r * 128;
+      const uint32_t p_addr = lane_addr + Cfg::TMEM_P + r * Cfg::P_STRIDE;
       const uint32_t o_addr = lane_addr + Cfg::TMEM_O + r * DMMA;
       float m_ref = -INFINITY, l = 0.f;
       bool ok = true;
@@ -184,6 +223,9 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_ld32(s_addr + 64, s + 64);
         tmem_ld32(s_addr + 96, s + 96);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_consumed[r]);  // S_r is in registers: the tensor core may overwrite it
         const int valid = n - j * 128;  // keys of this tile that exist
         if (valid < 128) {
 #pragma unroll
@@ -205,6 +247,10 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           // lazy rescale: keep the old reference unless the new maximum exceeds it by more than 2^8
           const bool need = mx > m_ref + 8.f;
           if (__any_sync(0xffffffffu, need)) {
+            // O_r must be quiescent: P_r(j-1) V_{j-1} has to be complete before the accumulator is rescaled
+            ok = mbar_wait_warp(&pv_done[r], (j - 1) & 1, &dead, p.err, 32);
+            if (!ok) break;
+            tc_fence_after();
             const float f = need ? fast_exp2(m_ref - mx) : 1.f;
             if (need) m_ref = mx;
             l *= f;
@@ -222,18 +268,22 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(s[c0 + 2 * i]), p.scale_log2, -m_ref));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(s[c0 + 2 * i + 1]), p.scale_log2, -m_ref));
-            l0 += p0;
-            l1 += p1;
-            pk[i] = pack_half2(p0, p1);
-          }
-          tmem_st16(s_addr + (c0 >> 1), pk);
+        for (int c = 0; c < 128; c += 2) {  // exp in place: the packed pair (c, c+1) lands in s[c/2]
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2, -m_ref));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -m_ref));
+          l0 += p0;
+          l1 += p1;
+          s[c >> 1] = pack_half2(p0, p1);
         }
+        if (j > 0) {  // the P_r buffer is free once P_r(j-1) V_{j-1} has completed (long done by now)
+          ok = mbar_wait_warp(&pv_done[r], (j - 1) & 1, &dead, p.err, 33);
+          if (!ok) break;
+          tc_fence_after();
+        }
+        tmem_st16(p_addr, s);
+        tmem_st16(p_addr + 16, s + 16);
+        tmem_st16(p_addr + 32, s + 32);
+        tmem_st16(p_addr + 48, s + 48);
         l += l0 + l1;
         tmem_st_wait();
         tc_fence_before();
@@ -242,7 +292,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       // -------- epilogue: O / l -> fp16, natural-log LSE --------
       ok = __all_sync(0xffffffffu, ok);
-      if (ok) ok = mbar_wait_warp(&o_full[r], 0, &dead, p.err, 31);
+      if (ok) ok = mbar_wait_warp(&pv_done[r], (T - 1) & 1, &dead, p.err, 31);
       if (ok) {
         tc_fence_after();
         const float inv = 1.f / l;
