@@ -91,6 +91,27 @@ class FeedForward(nn.Module):
         return self.net(x)
 
 
+_LN_MIXED = None
+
+
+def _layer_norm(norm: nn.LayerNorm, x: torch.Tensor) -> torch.Tensor:
+    """LayerNorm of an fp16 activation with fp32 statistics and fp32 affine parameters WITHOUT autocast's fp32 input
+    copy and fp32 output (the next Linear would cast it back to fp16 anyway): same rounding point, two copies fewer.
+    Falls back to the module call when this torch build has no mixed-dtype layer_norm kernel."""
+    global _LN_MIXED
+    if x.is_cuda and x.dtype == torch.float16 and norm.weight.dtype == torch.float32 and _LN_MIXED is not False:
+        try:
+            with torch.autocast("cuda", enabled=False):
+                y = F.layer_norm(x, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
+            _LN_MIXED = True
+            return y
+        except RuntimeError:
+            if _LN_MIXED:  # it worked before: a real error
+                raise
+            _LN_MIXED = False
+    return norm(x)
+
+
 def _fp16(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == torch.float16 else t.to(torch.float16)
 
@@ -282,9 +303,9 @@ class BasicTransformerBlock(nn.Module):
         c = self._cache
         B, n_obj = c["B"], c["n_obj"]
         a1 = self.attn1
-        x = a1.project_out(a1.self_attention_core(self.norm1(x))) + x  # attention.py:274
+        x = a1.project_out(a1.self_attention_core(_layer_norm(self.norm1, x))) + x  # attention.py:274
         a2 = self.attn2
-        q = _fp16(a2.to_q(self.norm2(x)))  # computed ONCE (the reference recomputes it 1 + n_obj times)
+        q = _fp16(a2.to_q(_layer_norm(self.norm2, x)))  # computed ONCE (the reference recomputes it 1 + n_obj times)
         coef_b = None
         if n_obj:
             coef_b = coef.reshape(-1, n_obj).to(device=x.device, dtype=torch.float32)
@@ -293,7 +314,7 @@ class BasicTransformerBlock(nn.Module):
             coef_b = coef_b.contiguous()
         blended = ops.dual_cross_attention(q, c["k"], c["v"], c["masks"], coef_b, a2.heads)  # :278-294, pre-to_out
         x = a2.project_out(blended) + x  # :281 + :297 (to_out commutes with the blend)
-        return self.ff(self.norm3(x)) + x  # :299
+        return self.ff(_layer_norm(self.norm3, x)) + x  # :299
 
 
 class SpatialTransformer(nn.Module):
@@ -314,7 +335,12 @@ class SpatialTransformer(nn.Module):
     def forward(self, x, context=None, time=None, text_index=None, coef=None, bboxs_curr=None):
         b, c, h, w = x.shape
         x_in = x
-        x = self.norm(x)
+        if x.is_cuda and x.dtype == torch.float16:  # fused NHWC GroupNorm (fp32 statistics), no activation here
+            nw = self.norm.weight if self.norm.weight.dtype == torch.float32 else self.norm.weight.float()
+            nb = self.norm.bias if self.norm.bias.dtype == torch.float32 else self.norm.bias.float()
+            x = ops.group_norm_silu(x, nw, nb, self.norm.eps, False)
+        else:
+            x = self.norm(x)
         x = self.proj_in(x)
         x = x.permute(0, 2, 3, 1).reshape(b, h * w, -1)  # 'b c h w -> b (h w) c'
         for block in self.transformer_blocks:

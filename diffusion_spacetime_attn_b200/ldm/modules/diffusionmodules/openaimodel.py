@@ -19,8 +19,21 @@ import torch as th
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .... import ops as _ops
 from ..attention import BasicTransformerBlock, SpatialTransformer
 from .util import checkpoint, conv_nd, linear, normalization, timestep_embedding, zero_module
+
+
+def _fusable(x) -> bool:
+    return x.is_cuda and x.dtype == th.float16
+
+
+def gn_silu(norm: nn.GroupNorm, x, silu: bool = True):
+    """GroupNorm32 (+ SiLU) on an fp16 CUDA activation through the fused NHWC kernel (csrc/sta_groupnorm.cu): fp32
+    statistics like the reference's `x.float()` path (util.py:214-216), one rounding to fp16."""
+    w = norm.weight if norm.weight.dtype == th.float32 else norm.weight.float()
+    b = norm.bias if norm.bias.dtype == th.float32 else norm.bias.float()
+    return _ops.group_norm_silu(x, w, b, norm.eps, silu)
 
 
 class TimestepBlock(nn.Module):
@@ -92,10 +105,14 @@ class ResBlock(TimestepBlock):
         return checkpoint(self._forward, (x, emb), self.parameters(), flag)
 
     def _forward(self, x, emb):
-        h = self.in_layers(x)
+        fused = _fusable(x)
+        h = self.in_layers[2](gn_silu(self.in_layers[0], x)) if fused else self.in_layers(x)
         emb_out = self.emb_layers(emb).type(h.dtype)
         h = h + emb_out[:, :, None, None]
-        h = self.out_layers(h)
+        if fused and _fusable(h):
+            h = self.out_layers[3](self.out_layers[2](gn_silu(self.out_layers[0], h)))  # [2] = Dropout(p)
+        else:
+            h = self.out_layers(h)
         return self.skip_connection(x) + h
 
 
@@ -211,5 +228,7 @@ class UNetModel(nn.Module):
         for module in self.output_blocks:
             h = th.cat([h, hs.pop()], dim=1)
             h = module(h, emb, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
+        if _fusable(h):  # GroupNorm32 works in fp32 either way; skipping the cast only skips two copies
+            return self.out[2](gn_silu(self.out[0], h))
         h = h.type(x.dtype)
         return self.out(h)

@@ -20,6 +20,8 @@ EXPORTED_SYMBOLS = (
     "sta_sattn_bwd",
     "sta_xattn_fwd",
     "sta_xattn_bwd",
+    "sta_groupnorm_fwd",
+    "sta_groupnorm_bwd",
     "sta_probe_gemm",
     "sta_probe_tmem_bw",
     "sta_debug_read",
@@ -77,6 +79,14 @@ class XattnBwdArgs(C.Structure):
     ]
 
 
+class GroupNormArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("d_out", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("out", C.c_void_p),
+        ("stats", C.c_void_p), ("bwd_stats", C.c_void_p),
+        ("batch", C.c_int32), ("hw", C.c_int32), ("channels", C.c_int32), ("silu", C.c_int32), ("eps", C.c_float),
+    ]
+
+
 class ProbeArgs(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("a_rows", C.c_int32), ("a_tensor_rows", C.c_int32), ("a_cols", C.c_int32),
@@ -110,7 +120,7 @@ def load() -> C.CDLL:
     for name, argt in (
         ("sta_sattn_fwd", SattnFwdArgs), ("sta_sattn_bwd", SattnBwdArgs),
         ("sta_xattn_fwd", XattnFwdArgs), ("sta_xattn_bwd", XattnBwdArgs),
-        ("sta_probe_gemm", ProbeArgs),
+        ("sta_probe_gemm", ProbeArgs), ("sta_groupnorm_fwd", GroupNormArgs), ("sta_groupnorm_bwd", GroupNormArgs),
     ):
         if not hasattr(lib, name):  # reported by tests/test_cabi.py; calling it raises AttributeError
             continue

@@ -13,7 +13,7 @@ import torch
 from . import native
 
 # number of kernels launched by this module since import (bench.py reports it as `gpu_launches`)
-LAUNCHES = {"sattn_fwd": 0, "sattn_bwd": 0, "xattn_fwd": 0, "xattn_bwd": 0}
+LAUNCHES = {"sattn_fwd": 0, "sattn_bwd": 0, "xattn_fwd": 0, "xattn_bwd": 0, "groupnorm_fwd": 0, "groupnorm_bwd": 0}
 
 
 def launch_count() -> int:
@@ -279,3 +279,63 @@ def self_attention(q, k, v, heads):
 
 def dual_cross_attention(q, k_ctx, v_ctx, mask, coef, heads):
     return DualCrossAttentionFn.apply(q, k_ctx, v_ctx, mask, coef, heads)
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused GroupNorm(32) [+ SiLU], NHWC fp16
+# ------------------------------------------------------------------------------------------------------
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[B, C, H, W] tensor whose memory is NHWC-dense (channels_last); copies only if it is not already."""
+    return x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+
+
+def groupnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool):
+    _require(x, "x")
+    _require(gamma, "gamma", torch.float32)
+    _require(beta, "beta", torch.float32)
+    b, c, h, w = x.shape
+    x = _nhwc(x)
+    out = torch.empty_like(x, memory_format=torch.channels_last)
+    stats = torch.empty((b, 32, 2), device=x.device, dtype=torch.float32)
+    a = native.GroupNormArgs()
+    a.x, a.gamma, a.beta, a.out, a.stats = x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), stats.data_ptr()
+    a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
+    with _timed("groupnorm_fwd", (b, h * w, c)):
+        native.check(native.load().sta_groupnorm_fwd(C.byref(a), _stream()), "sta_groupnorm_fwd")
+    LAUNCHES["groupnorm_fwd"] += 2
+    return out, stats, x
+
+
+def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool):
+    b, c, h, w = x.shape
+    d_out = _nhwc(d_out if d_out.dtype == torch.float16 else d_out.to(torch.float16))
+    d_x = torch.empty_like(x, memory_format=torch.channels_last)
+    bstats = torch.empty((b, 32, 2), device=x.device, dtype=torch.float32)
+    a = native.GroupNormArgs()
+    a.x, a.d_out, a.gamma, a.beta, a.out = x.data_ptr(), d_out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), d_x.data_ptr()
+    a.stats, a.bwd_stats = stats.data_ptr(), bstats.data_ptr()
+    a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
+    with _timed("groupnorm_bwd", (b, h * w, c)):
+        native.check(native.load().sta_groupnorm_bwd(C.byref(a), _stream()), "sta_groupnorm_bwd")
+    LAUNCHES["groupnorm_bwd"] += 2
+    return d_x
+
+
+class GroupNormSiLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, silu):
+        out, stats, x_nhwc = groupnorm_fwd(x, gamma, beta, eps, silu)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(x_nhwc, gamma, beta, stats)
+            ctx.eps, ctx.silu = eps, silu
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, gamma, beta, stats = ctx.saved_tensors
+        return groupnorm_bwd(x, d_out, gamma, beta, stats, ctx.eps, ctx.silu), None, None, None, None
+
+
+def group_norm_silu(x, gamma, beta, eps=1e-5, silu=True):
+    """GroupNorm(32)(x.float()).half() [-> SiLU] in one pass; x fp16 [B, C, H, W] (any layout, NHWC is free)."""
+    return GroupNormSiLUFn.apply(x, gamma, beta, eps, silu)

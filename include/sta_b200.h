@@ -143,6 +143,30 @@ typedef struct {
 int sta_xattn_bwd(const sta_xattn_bwd_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Fused GroupNorm(32 groups) [+ SiLU] on NHWC fp16 activations, fp32 statistics (reference GroupNorm32 + nn.SiLU:
+ * ldm/modules/diffusionmodules/util.py:214-216 with openaimodel.py:206-236, 681-685 and attention.py:317).
+ *   x, out  fp16 [batch, hw, channels] (the memory of a channels_last [batch, channels, h, w] tensor)
+ *   gamma, beta  f32 [channels]
+ *   stats   f32 [batch, 32, 2]  written by the forward (raw sum / sum of squares per group), read by the backward
+ * Backward produces d(x) only (the UNet weights are frozen): out = d_x, d_out = upstream gradient, bwd_stats is a
+ * f32 [batch, 32, 2] workspace.  channels must be a multiple of 32 and of 8.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  const void* d_out; /* backward only */
+  const float* gamma;
+  const float* beta;
+  void* out;
+  float* stats;
+  float* bwd_stats; /* backward only */
+  int32_t batch, hw, channels, silu;
+  float eps;
+} sta_groupnorm_args;
+
+int sta_groupnorm_fwd(const sta_groupnorm_args* args, void* stream);
+int sta_groupnorm_bwd(const sta_groupnorm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Test hook: one tcgen05 GEMM tile with caller-supplied UMMA descriptors (tests/test_probe_gpu.py pins the
  * shared-memory/TMEM operand encodings the kernels above rely on).  Not part of the product path.
  * ------------------------------------------------------------------------------------------------------- */

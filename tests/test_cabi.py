@@ -60,7 +60,7 @@ def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
 
 @pytest.mark.parametrize("struct,cname", [("SattnFwdArgs", "sta_sattn_fwd_args"), ("SattnBwdArgs", "sta_sattn_bwd_args"),
                                           ("XattnFwdArgs", "sta_xattn_fwd_args"), ("XattnBwdArgs", "sta_xattn_bwd_args"),
-                                          ("ProbeArgs", "sta_probe_args")])
+                                          ("ProbeArgs", "sta_probe_args"), ("GroupNormArgs", "sta_groupnorm_args")])
 def test_ctypes_structs_mirror_the_header(struct, cname):
     from diffusion_spacetime_attn_b200 import native
 

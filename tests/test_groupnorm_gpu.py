@@ -1,0 +1,53 @@
+"""GPU parity: fused NHWC GroupNorm(32) [+ SiLU] forward / input-gradient backward (sta_groupnorm_*) against the
+reference's GroupNorm32 arithmetic (x.float() -> group_norm -> [SiLU]) evaluated by torch on the CPU in fp32 on the
+same fp16-rounded inputs.  Tolerance: |err| <= 2e-3 + 4e-3 |ref| forward (one fp16 rounding), 3e-3 max|ref| + 1e-2 |ref| backward."""
+from __future__ import annotations
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffusion_spacetime_attn_b200 import native, ops
+
+# (batch, channels, h, w): every channel count the SD-v1 UNet normalises, at 512^2 and odd sizes
+SHAPES = [(2, 320, 64, 64), (2, 640, 32, 32), (2, 1280, 16, 16), (2, 1280, 8, 8), (2, 2560, 8, 8), (2, 1920, 16, 16),
+          (2, 960, 32, 32), (2, 640, 64, 64), (1, 320, 12, 12), (3, 64, 5, 7)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("silu", [True, False])
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
+def test_groupnorm_silu_fwd_bwd(shape, silu):
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(c + h)
+    x = (torch.randn(b, c, h, w, generator=g) * 1.5 + 0.3).half()
+    gamma = 1 + 0.1 * torch.randn(c, generator=g)
+    beta = 0.1 * torch.randn(c, generator=g)
+    dy = (torch.randn(b, c, h, w, generator=g) * 0.1).half()
+    xf = x.float().requires_grad_(True)
+    ref = F.group_norm(xf, 32, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    (ref * dy.float()).sum().backward()
+    xd = x.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
+    y = ops.group_norm_silu(xd, gamma.cuda(), beta.cuda(), 1e-5, silu)
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    assert y.is_contiguous(memory_format=torch.channels_last) or min(h, w, c) == 1
+    err = (y.float().cpu() - ref.detach()).abs()
+    assert (err <= 2e-3 + 4e-3 * ref.detach().abs()).all(), f"fwd max err {err.max().item():.3e}"
+    gref = xf.grad
+    gerr = (xd.grad.float().cpu() - gref).abs()
+    assert (gerr <= 3e-3 * gref.abs().max() + 1e-2 * gref.abs()).all(), f"bwd max err {gerr.max().item():.3e} (ref max {gref.abs().max().item():.3e})"
+
+
+@pytest.mark.gpu
+def test_groupnorm_accepts_nchw_input_and_rejects_bad_channels():
+    x = torch.randn(2, 320, 16, 16).half().cuda()  # NCHW-contiguous: converted once
+    gamma, beta = torch.ones(320).cuda(), torch.zeros(320).cuda()
+    y = ops.group_norm_silu(x, gamma, beta, 1e-5, False)
+    ref = F.group_norm(x.float(), 32, gamma, beta, 1e-5)
+    assert (y.float() - ref).abs().max().item() < 5e-3
+    with pytest.raises(RuntimeError, match="multiple of 32"):
+        ops.group_norm_silu(torch.randn(1, 48, 4, 4).half().cuda(), torch.ones(48).cuda(), torch.zeros(48).cuda())
