@@ -113,6 +113,7 @@ class SpaceTimeAttnPipeline:
         from . import native
 
         native.load()  # fail loudly before building 4 GB of networks if the CUDA library is missing
+        torch.backends.cudnn.benchmark = True  # fixed shapes for 150+ evaluations per image: let cuDNN pick its best kernels
         self.device = torch.device(device)
         self.steps, self.scale, self.latent_size = steps, scale, latent_size
         torch.manual_seed(seed)
