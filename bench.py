@@ -238,7 +238,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "SD-v1-4 512x512, 50 PLMS steps, 2 objects, alpha inner-opt (3 epochs), batch=1"},
+        "config": {"workload": "BASELINE.json configs[1]: SD-v1-4 architecture 512x512, %d PLMS steps, 2-3 objects, "
+                               "alpha inner-opt on (%d epochs), batch=1 per GPU" % (args.ddim_steps, args.epochs)},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }

@@ -231,3 +231,42 @@ def test_cuda_graph_execution_matches_eager_alpha_optimisation():
         assert (w_g - w_e).abs().max().item() < 0.1 * dw_e.abs().max().item() + 1e-4
         assert abs(l_g[0][0] - l_e[0][0]) < 2e-2 * abs(l_e[0][0]) + 1e-2
     assert (results["graph"][0][0] - results["graph"][1][0]).abs().max() > 1e-2  # different prompts, different latents
+
+
+@pytest.mark.gpu
+def test_config5_shape_ddim_two_prompts_six_objects_matches_oracle():
+    """BASELINE.json configs[4] in miniature: DDIM + injection (an extension, see ldm/models/diffusion/ddim.py), B = 2
+    prompts per call with DIFFERENT layouts, 6 local descriptions each, a latent whose token counts (576 / 144) are not
+    multiples of the 128-row tiles.  Checked against the oracle evaluated per prompt (B = 1 semantics of the reference)."""
+    from diffusion_spacetime_attn_b200.ldm.models.diffusion.ddim import DDIMSampler
+
+    m, sd, cfg = _tiny_models(6)
+    ld = LatentDiffusion(unet_config={"params": dict(TINY)}, build_first_stage=False)
+    ld.model.diffusion_model = m
+    ld = ld.cuda().eval().requires_grad_(False)
+    S, lat, B, n_obj = 4, 24, 2, 6
+    g = torch.Generator().manual_seed(21)
+    x_T = torch.randn(B, 4, lat, lat, generator=g)
+    uc = uncond().expand(B, -1, -1).contiguous()
+    c = torch.cat([ctx_tensor(300), ctx_tensor(301)])
+    locs = [torch.cat([ctx_tensor(310 + i), ctx_tensor(320 + i)]) for i in range(n_obj)]  # each [B, 77, 768]
+    boxes = [[[0.2 + 0.12 * i, 0.3 + 0.08 * i] for i in range(n_obj)], [[0.8 - 0.1 * i, 0.25 + 0.1 * i] for i in range(n_obj)]]
+    alpha = torch.full((n_obj, S), 5.0 / n_obj)
+    sampler = DDIMSampler(ld, clip_loss_model=torch.nn.Identity(), save_images=False)
+    with torch.autocast("cuda"):
+        sampler.sample(S=S, batch_size=B, shape=[4, lat, lat], conditioning=c.cuda(), x_T=x_T.cuda(),
+                       unconditional_guidance_scale=7.5, unconditional_conditioning=uc.cuda(), text_index=0,
+                       curr_text=["p0", "p1"], bboxs_curr=boxes, seed=1, prompt_idx=[0, 1],
+                       object_names=[["o"] * n_obj] * B, local_conditionings=[l.cuda() for l in locs],
+                       optimize_alpha=False)
+    got = sampler.last_result["latent"].float().cpu()
+    assert native.device_error() == 0
+    sch = O.make_schedule(S)
+    for b in range(B):  # oracle: one prompt at a time, DDIM update = PLMS update with e_t' = e_t
+        img = x_T[b:b + 1]
+        for i, step in enumerate(np.flip(sch.timesteps)):
+            index = S - i - 1
+            e = O.guided_eps(img, int(step), alpha[:, i], uc[b:b + 1], c[b:b + 1], [l[b:b + 1] for l in locs], uncond(),
+                             boxes[b], sd, cfg)
+            img, _ = O.plms_update(img, e, sch, index)
+        assert rel_l2(got[b:b + 1], img) < 1e-2, f"prompt {b}"
