@@ -50,7 +50,21 @@ struct SattnBwdCfg {
   static constexpr int DS_BYTES = 2 * kSBBlockBytes;  // dS^T: 128 keys x 128 queries fp16
   static constexpr int STAGE_BYTES = PIPE_DRAIN ? 128 * D * 4 : 0;  // fp32 dQ tile staged for the TMA reduce-add
   static constexpr int SMEM_TOTAL = 2 * TILE + 2 * ST * TILE + NDS * DS_BYTES + STAGE_BYTES + 1024;
-  static constexpr int THREADS = 64 + 256;  // TMA warp, MMA warp, two math warpgroups
+  // Math warpgroups: query tile i is handled as two half-tiles (64 query columns each, the MMA granularity); with
+  // NWG = 4 each half is shared by two warpgroups (32 columns each) so that every scheduler has four math warps to
+  // hide the LDS / MUFU / TMEM latencies (with two the math phase ran at 43 % MUFU, 47 % issue utilisation).
+  static constexpr int NWG = (MODE == 2) ? 4 : 2;
+  static constexpr int CW = 128 / NWG;              // query columns per warpgroup
+  static constexpr int CH = (NWG == 4) ? 16 : 32;   // columns per TMEM load / inner chunk (register budget)
+  static constexpr int DQ_W0 = (NWG == 4) ? 16 : 24;             // head-dim columns drained by warpgroup 0
+  static constexpr int DQ_W1 = (NWG == 4) ? 8 : (D > 24 ? D - 24 : 8);  // ... by every other warpgroup
+  // P^T (packed fp16, A operand of dV += P^T dO): over the S^T columns of its half-tile when ONE warpgroup owns the
+  // half (NWG = 2); with two warpgroups per half that aliasing would race (one group's P^T lands on S^T columns the
+  // other has not read yet), so P^T gets its own 64 columns: 256 + 4*48 + 64 = 512.
+  static constexpr int TMEM_P = (NWG == 4) ? 448 : 0;
+  static constexpr int P_HALF = (NWG == 4) ? 32 : 64;  // TMEM columns between the P^T of half 0 and half 1
+  static_assert(NWG == 2 || 256 + 4 * NACC_MAX + 64 <= 512, "TMEM budget");
+  static constexpr int THREADS = 64 + 128 * NWG;  // TMA warp, MMA warp, math warpgroups
 };
 
 struct SattnBwdParams {
@@ -96,7 +110,10 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ uint64_t kv_full, qdo_full[ST], qdo_empty[ST], sdp_full[2], pds_ready[2], dq_full, dq_drained;
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
-  __shared__ __align__(16) float s_lse2[128], s_delta[128];  // lse*log2e and delta of the current query tile
+  // -lse*log2e and -delta*scale of the current query tile; double-buffered when there are four warpgroups (no
+  // named-barrier ids left for a "done reading" barrier per group, and no need for one then)
+  constexpr int NSB = (Cfg::NWG == 4) ? 2 : 1;
+  __shared__ __align__(16) float s_lse2_buf[NSB][128], s_delta_buf[NSB][128];
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -108,9 +125,9 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     dead = 0;
     mbar_init(&kv_full, 1);
     for (int i = 0; i < ST; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&pds_ready[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&pds_ready[i], 2 * Cfg::NWG); }
     mbar_init(&dq_full, 1);
-    mbar_init(&dq_drained, 8);
+    mbar_init(&dq_drained, 4 * Cfg::NWG);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -198,7 +215,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dV += P^T_half dO_half   (K = 64 queries of this half)
-            umma_ts_w(tmem + Cfg::TMEM_DV, tmem + hf * 64 + k * 8,
+            umma_ts_w(tmem + Cfg::TMEM_DV, tmem + Cfg::TMEM_P + hf * Cfg::P_HALF + k * 8,
                     umma_desc(mndesc_hi, do_addr + col_off + hf * 8192 + k * 2048), idesc_acc, i > 0 || hf > 0 || k > 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // dK += dS^T_half Q_half
@@ -238,7 +255,9 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
   } else {
     // ===================================== per-key-row math ==================================
-    const int g = (warp - 2) >> 2;           // math warpgroup = query half
+    constexpr int NWG = Cfg::NWG, CW = Cfg::CW, CH = Cfg::CH;
+    const int g = (warp - 2) >> 2;           // math warpgroup: query columns [g*CW, (g+1)*CW) of the tile
+    const int hf = g / (NWG / 2);            // the half-tile (MMA granularity) those columns belong to
     const int r = ((warp & 3) << 5) + lane;  // key row for S^T/dP^T/dK/dV, query row for dQ_i
     const int t128 = tid - 64 - g * 128;     // 0..127 inside the warpgroup
     const int key = j * 128 + r;
@@ -254,9 +273,9 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         // TMEM -> fp32 smem tile -> ONE TMA reduce-add per warpgroup and tile (the per-thread red.global path below
         // costs ~1500 cycles per tile in LSU back-pressure; the bulk reduction is asynchronous).  Warpgroup 0 owns
         // head-dim columns [0, 24), warpgroup 1 columns [24, D): no synchronisation between the warpgroups.
-        constexpr int W0 = 24, W1 = D - 24;
-        const int wcols = g == 0 ? W0 : W1, cbase = g == 0 ? 0 : W0;
-        float* stage = sStage + (g == 0 ? 0 : 128 * W0);
+        constexpr int W0 = Cfg::DQ_W0, W1 = Cfg::DQ_W1;
+        const int wcols = g == 0 ? W0 : W1, cbase = g == 0 ? 0 : W0 + (g - 1) * W1;
+        float* stage = sStage + 128 * cbase;
         if (t128 == 0) bulk_wait_group_read0();  // this warpgroup's previous reduce has finished reading its tile
         named_bar_sync(5 + g, 128);
 #pragma unroll
@@ -270,7 +289,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           d4[1] = make_float4(__uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]), __uint_as_float(o[7]));
         }
         fence_proxy_async_smem();
-        named_bar_sync(7 + g, 128);
+        named_bar_sync(5 + NWG + g, 128);
         if (t128 == 0 && !(p.dbg & 1)) {
           tma_reduce_add_4d(g == 0 ? &tm_dq : &tm_dq1, stage, cbase, h, q0row, b);  // OOB rows are clipped by TMA
           bulk_commit_group();
@@ -280,7 +299,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const int qrow = q0row + r;
       float* dst = p.dq_accum + ((long long)b * n + qrow) * (p.heads * D) + h * D + col0;
 #pragma unroll
-      for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 16) {
+      for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 8 * NWG) {
         const int cc = c0 + 8 * g;
         if (cc >= ncols) break;
         uint32_t o[8];
@@ -295,8 +314,9 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // per-thread prefetch of one staged statistic: threads 0..63 of a warpgroup own -lse*log2e, 64..127 own -delta*scale
     auto load_stat = [&](int it_n) -> float {
       if (it_n >= total) return 0.f;
-      const int qi = (it_n % T) * 128 + g * 64 + (t128 & 63);
-      if (t128 < 64) return qi < n ? -lse_bh[qi] * 1.4426950408889634f : -INFINITY;
+      if (t128 >= 2 * CW) return 0.f;
+      const int qi = (it_n % T) * 128 + g * CW + (t128 % CW);
+      if (t128 < CW) return qi < n ? -lse_bh[qi] * 1.4426950408889634f : -INFINITY;
       return qi < n ? -delta_bh[qi] * p.scale : 0.f;
     };
     float pre_val = load_stat(0);
@@ -309,30 +329,36 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const int ncols = (Cfg::NPASS == 1) ? D : (pass == 0 ? 128 : D - 128);   // columns of this pass
       // stage lse / delta of this warpgroup's 64 query columns for broadcast reads (values were prefetched from
       // global memory one tile ahead, so the load latency is off the critical path)
-      {
-        const int c = t128 & 63;
-        if (t128 < 64) s_lse2[g * 64 + c] = pre_val;
-        else s_delta[g * 64 + c] = pre_val;
-      }
+      float* s_lse2 = s_lse2_buf[it % NSB];
+      float* s_delta = s_delta_buf[it % NSB];
+      if (t128 < CW) s_lse2[g * CW + t128] = pre_val;
+      else if (t128 < 2 * CW) s_delta[g * CW + t128 - CW] = pre_val;
       named_bar_sync(1 + g, 128);
       pre_val = load_stat(it + 1);
       tt = clock64();
-      ok = mbar_wait_warp(&sdp_full[g], it & 1, &dead, p.err, 30);
+      ok = mbar_wait_warp(&sdp_full[hf], it & 1, &dead, p.err, 30);
       if (!ok) break;
       tc_fence_after();
       c_wait_sdp += clock64() - tt; tt = clock64();
-      const float* lse2 = s_lse2 + g * 64;
-      const float* dlt = s_delta + g * 64;
-      unsigned char* ds_blk = sDS + (it % Cfg::NDS) * Cfg::DS_BYTES + g * kSBBlockBytes;
+      const float* lse2 = s_lse2 + g * CW;
+      const float* dlt = s_delta + g * CW;
+      // dS^T block of this half-tile; this warpgroup's columns start at 16-byte chunk (g*CW % 64) / 8 of each row
+      unsigned char* ds_blk = sDS + (it % Cfg::NDS) * Cfg::DS_BYTES + hf * kSBBlockBytes;
+      const int col_in_half = (g * CW) & 63;
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t s[32], dp[32];
-        tmem_ld32(lane_addr + g * 64 + c0, s);
-        tmem_ld32(lane_addr + 128 + g * 64 + c0, dp);
+      for (int c0 = 0; c0 < CW; c0 += CH) {
+        uint32_t s[CH], dp[CH];
+        if (CH == 32) {
+          tmem_ld32(lane_addr + g * CW + c0, s);
+          tmem_ld32(lane_addr + 128 + g * CW + c0, dp);
+        } else {
+          tmem_ld16(lane_addr + g * CW + c0, s);
+          tmem_ld16(lane_addr + 128 + g * CW + c0, dp);
+        }
         tmem_ld_wait();
-        uint32_t pk[16], dk[16];
+        uint32_t pk[CH / 2], dk[CH / 2];
 #pragma unroll
-        for (int q = 0; q < 32; q += 4) {
+        for (int q = 0; q < CH; q += 4) {
           const float4 nl = *reinterpret_cast<const float4*>(lse2 + c0 + q);   // broadcast reads, 4 columns at a time
           const float4 nd = *reinterpret_cast<const float4*>(dlt + c0 + q);
           const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, ndv[4] = {nd.x, nd.y, nd.z, nd.w};
@@ -350,13 +376,15 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         if (!key_ok) {  // keys past the end of the sequence (last tile only): P = dS = 0
 #pragma unroll
-          for (int e = 0; e < 16; ++e) { pk[e] = 0u; dk[e] = 0u; }
+          for (int e = 0; e < CH / 2; ++e) { pk[e] = 0u; dk[e] = 0u; }
         }
-        tmem_st16(lane_addr + g * 64 + (c0 >> 1), pk);
-        // dS^T row r, query columns [64 g + c0, +32): four 16-byte chunks of block g
-        const int chunk0 = c0 >> 3;
+        // P^T (packed fp16): query column c of the half-tile -> TMEM column TMEM_P + hf*P_HALF + c/2
+        if (CH == 32) tmem_st16(lane_addr + Cfg::TMEM_P + hf * Cfg::P_HALF + ((col_in_half + c0) >> 1), pk);
+        else tmem_st8(lane_addr + Cfg::TMEM_P + hf * Cfg::P_HALF + ((col_in_half + c0) >> 1), pk);
+        // dS^T row r, query columns [g*CW + c0, +CH): CH/8 16-byte chunks of the half-tile's smem block
+        const int chunk0 = (col_in_half + c0) >> 3;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < CH / 8; ++cc) {
           uint4 v = make_uint4(dk[4 * cc], dk[4 * cc + 1], dk[4 * cc + 2], dk[4 * cc + 3]);
           if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(ds_blk + sw128_offset(r, chunk0 + cc)) = v;
         }
@@ -372,8 +400,8 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (!ok) break;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pds_ready[g]);
-      named_bar_sync(3 + g, 128);  // the warpgroup is done reading its lse / delta staging area
+      if (lane == 0) mbar_arrive(&pds_ready[hf]);
+      if (NSB == 1) named_bar_sync(3 + g, 128);  // the warpgroup is done reading its lse / delta staging area
       c_comp += clock64() - tt; tt = clock64();
       // ---- drain dQ into the fp32 accumulator: the warpgroups take alternate 8-column chunks.  With PIPE_DRAIN the
       //      tile drained here is the PREVIOUS one (its MMAs finished while this tile's P/dS math ran) ----
@@ -397,7 +425,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         __half* dk_row = p.d_k + ((long long)b * n + key) * (p.heads * D) + h * D + col0;
         __half* dv_row = p.d_v + ((long long)b * n + key) * (p.heads * D) + h * D + col0;
 #pragma unroll
-        for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 16) {
+        for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 8 * NWG) {
           const int cc = c0 + 8 * g;
           if (cc >= ncols) break;
           uint32_t a[8], c[8];
@@ -497,7 +525,7 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   CUtensorMap tm_dq, tm_dq1;
   {
     const uint64_t st[4] = {4, (uint64_t)D * 4, (uint64_t)C * 4, (uint64_t)a->n * C * 4};
-    const uint32_t bx0[4] = {24, 1, 128, 1}, bx1[4] = {(uint32_t)(D > 24 ? D - 24 : 8), 1, 128, 1};
+    const uint32_t bx0[4] = {(uint32_t)Cfg::DQ_W0, 1, 128, 1}, bx1[4] = {(uint32_t)Cfg::DQ_W1, 1, 128, 1};
     if ((rc = make_tmap_f32_dense(&tm_dq, a->dq_accum, 4, dims, st, bx0))) return rc;
     if ((rc = make_tmap_f32_dense(&tm_dq1, a->dq_accum, 4, dims, st, bx1))) return rc;
   }

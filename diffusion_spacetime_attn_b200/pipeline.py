@@ -113,7 +113,11 @@ class SpaceTimeAttnPipeline:
         from . import native
 
         native.load()  # fail loudly before building 4 GB of networks if the CUDA library is missing
-        torch.backends.cudnn.benchmark = True  # fixed shapes for 150+ evaluations per image: let cuDNN pick its best kernels
+        # fixed shapes for 150+ evaluations per image: let cuDNN pick its best kernels (off under ncu: the autotuner's
+        # trial launches would all be serialised by the profiler)
+        import os
+
+        torch.backends.cudnn.benchmark = os.environ.get("STA_CUDNN_BENCHMARK", "1") == "1"
         self.device = torch.device(device)
         self.steps, self.scale, self.latent_size = steps, scale, latent_size
         torch.manual_seed(seed)

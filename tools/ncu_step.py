@@ -6,8 +6,11 @@
 The profiled region (cudaProfilerStart/Stop) is one generate() call AFTER a warm-up call captured the CUDA graphs, so
 the list contains exactly the kernels of the timed region of bench.py, in the same proportions per UNet evaluation.
 """
+import os
 import sys
 from pathlib import Path
+
+os.environ.setdefault("STA_CUDNN_BENCHMARK", "0")  # no autotuner trial launches under the profiler
 
 import torch
 
