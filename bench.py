@@ -342,12 +342,16 @@ def run_native(args):
     kernels = []
     if hist_graph:
         for (kind, key), n in hist_graph.items():
+            if not (kind.startswith("groupnorm") or kind.startswith("sattn") or kind.startswith("xattn")):
+                continue  # token-major streaming kernels (LayerNorm / GEGLU / bias adds): counted in gpu_launches only
             ms = standalone_kernel_ms(kind, key)
             kernels.append({"kernel": "sta_" + kind, "geometry": list(key), "launches": n, "total_ms": ms * n,
                             "mean_us": 1000.0 * ms, "tflops": launch_flops(kind, key) / ms / 1e9,
                             "gbs": launch_bytes(kind, key) / ms / 1e6, "timing": "standalone x launches"})
     else:
         for (kind, key), (n, tot) in ops.kernel_time_summary(records_k).items():
+            if not (kind.startswith("groupnorm") or kind.startswith("sattn") or kind.startswith("xattn")):
+                continue
             kernels.append({"kernel": "sta_" + kind, "geometry": list(key), "launches": n, "total_ms": tot,
                             "mean_us": 1000.0 * tot / n, "tflops": launch_flops(kind, key) / (tot / n) / 1e9,
                             "gbs": launch_bytes(kind, key) / (tot / n) / 1e6, "timing": "events in step"})

@@ -72,7 +72,8 @@ struct SattnBwdParams {
   const float* delta;  // [b, h, n]
   float* dq_accum;     // [b, n, h*D] fp32
   __half* d_k;
-  __half* d_v;         // [b, n, h*D] fp16 contiguous
+  __half* d_v;         // [b, n, h*D] fp16, token stride d_tok (batch stride n * d_tok)
+  long long d_tok;
   int n, heads;
   float scale, scale_log2;
   unsigned int* err;
@@ -422,8 +423,8 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       if (i == T - 1) {
         // ---- end of a pass: dK, dV columns [col0, col0 + ncols) of this key row (dq_full => all MMAs completed) ----
-        __half* dk_row = p.d_k + ((long long)b * n + key) * (p.heads * D) + h * D + col0;
-        __half* dv_row = p.d_v + ((long long)b * n + key) * (p.heads * D) + h * D + col0;
+        __half* dk_row = p.d_k + ((long long)b * n + key) * p.d_tok + h * D + col0;
+        __half* dv_row = p.d_v + ((long long)b * n + key) * p.d_tok + h * D + col0;
 #pragma unroll
         for (int c0 = 0; c0 < Cfg::NACC_MAX; c0 += 8 * NWG) {
           const int cc = c0 + 8 * g;
@@ -494,14 +495,17 @@ __global__ void sattn_delta_kernel(const __half* __restrict__ o, const __half* _
   delta[((long long)b * heads + h) * n + i] = acc;
 }
 
-__global__ void sattn_dq_cast_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, long long n4) {
+// dq_accum fp32 [rows, c] dense -> d_q fp16 [rows, c] with row stride d_tok (d_q may be a slice of one d(qkv) buffer)
+__global__ void sattn_dq_cast_kernel(const float4* __restrict__ src, __half* __restrict__ dst, long long n4, int c4,
+                                     long long d_tok) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n4) return;
   const float4 v = src[idx];
   uint2 o;
   o.x = pack_half2(v.x, v.y);
   o.y = pack_half2(v.z, v.w);
-  dst[idx] = o;
+  const long long row = idx / c4;
+  *reinterpret_cast<uint2*>(dst + row * d_tok + (idx - row * c4) * 4) = o;
 }
 
 template <int D>
@@ -541,6 +545,7 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   p.dq_accum = a->dq_accum;
   p.d_k = reinterpret_cast<__half*>(a->d_k);
   p.d_v = reinterpret_cast<__half*>(a->d_v);
+  p.d_tok = a->dqkv_token_stride > 0 ? a->dqkv_token_stride : C;
   p.n = a->n;
   p.heads = a->heads;
   p.scale = a->scale;
@@ -557,8 +562,8 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   STA_CUDA_CHECK(cudaGetLastError());
 
   const long long n4 = (long long)a->batch * a->n * C / 4;
-  sattn_dq_cast_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(a->dq_accum),
-                                                                        reinterpret_cast<uint2*>(a->d_q), n4);
+  sattn_dq_cast_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(a->dq_accum), reinterpret_cast<__half*>(a->d_q), n4, (int)(C / 4), p.d_tok);
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }
@@ -578,6 +583,9 @@ extern "C" int sta_sattn_bwd(const sta_sattn_bwd_args* a, void* stream) {
   if (a->batch < 1 || a->n < 1 || a->heads < 1) return fail(STA_ERR_BAD_ARG, "sta_sattn_bwd: empty shape");
   if ((a->o_token_stride % 8) || (a->o_batch_stride % 8) || (a->do_token_stride % 8) || (a->do_batch_stride % 8))
     return fail(STA_ERR_UNSUPPORTED, "sta_sattn_bwd: out/d_out rows must be 16-byte aligned");
+  if (a->dqkv_token_stride < 0 || (a->dqkv_token_stride % 8) ||
+      (a->dqkv_token_stride > 0 && a->dqkv_token_stride < (int64_t)a->heads * a->head_dim))
+    return fail(STA_ERR_BAD_ARG, "sta_sattn_bwd: dqkv_token_stride must be 0 (dense) or a multiple of 8 >= heads*head_dim");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (a->head_dim) {
     case 40: return launch_sattn_bwd<40>(a, s);

@@ -1,0 +1,357 @@
+// sta_tokens.cu — streaming kernels on token-major fp16 activations [rows, channels] of the transformer block:
+//
+//   sta_add_layernorm_fwd/bwd   s = x (+ bias) (+ residual);  y = LayerNorm(s)      (reference attention.py:274, 281/297, 299:
+//                               `attn(norm(x)) + x` followed by the next `norm`; under autocast the reference runs
+//                               LayerNorm in fp32 on an fp32 COPY of the fp16 activation and copies the fp32 result back
+//                               to fp16 for the next Linear — add + copy + LN + copy = 4 launches, 26 B per element; here
+//                               1 launch, 8 B per element, statistics still fp32)
+//   sta_geglu_fwd/bwd           out = value * gelu(gate) of GEGLU.proj's [rows, 2*inner] output (attention.py:47-49, exact
+//                               erf GELU as F.gelu) and d(proj) from d(out) in one pass (the reference's autograd runs
+//                               gelu_backward + 2 mul + cat)
+//
+// All four are HBM-bound: 16-byte vectors, one warp per row for the LayerNorm (row kept in registers between the
+// statistics and the normalisation: one read of the inputs, one write of each output), grid-stride vectors for GEGLU.
+// Only d(input) is produced in backward — the UNet weights are frozen during the alpha optimisation.
+#include "../../include/sta_b200.h"
+#include "sta_common.cuh"
+#include "sta_host.h"
+
+namespace sta {
+
+__device__ __forceinline__ void tk_unpack8(const uint4& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ uint4 tk_pack8(const float* f) {
+  uint4 o;
+  o.x = pack_half2(f[0], f[1]);
+  o.y = pack_half2(f[2], f[3]);
+  o.z = pack_half2(f[4], f[5]);
+  o.w = pack_half2(f[6], f[7]);
+  return o;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void load8f(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+struct LnParams {
+  const __half* x;
+  const float* bias;
+  const __half* res;
+  const float* gamma;
+  const float* beta;
+  __half* sum_out;
+  __half* y;
+  float* stats;
+  // backward
+  const __half* dy;
+  const __half* dsum;
+  __half* dx;
+  int rows, c;
+  float eps;
+};
+
+constexpr int kLnWarps = 4;
+
+// one warp per row; lane owns vectors lane, lane+32, ... (NV of them, the tail predicated off)
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int vecs = p.c >> 3;
+  const long long base = (long long)row * p.c;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+      tk_unpack8(*reinterpret_cast<const uint4*>(p.x + base + vi * 8), v[i]);
+      bool rounded = true;
+      if (p.res) {
+        float r[8];
+        tk_unpack8(*reinterpret_cast<const uint4*>(p.res + base + vi * 8), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+        rounded = false;
+      }
+      if (p.bias) {
+        float b[8];
+        load8f(p.bias + vi * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += b[j];
+        rounded = false;
+      }
+      if (!rounded) {  // the sum is stored in fp16; normalise exactly what the backward will read back
+        const uint4 o = tk_pack8(v[i]);
+        if (p.sum_out) *reinterpret_cast<uint4*>(p.sum_out + base + vi * 8) = o;
+        tk_unpack8(o, v[i]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  if (!p.gamma) return;
+  const float inv_c = 1.f / (float)p.c;
+  const float mean = warp_sum(s) * inv_c;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) * inv_c + p.eps);
+  if (p.stats && lane == 0) *reinterpret_cast<float2*>(p.stats + 2 * (long long)row) = make_float2(mean, rstd);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+      float g[8], b[8], o[8];
+      load8f(p.gamma + vi * 8, g);
+      load8f(p.beta + vi * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
+      *reinterpret_cast<uint4*>(p.y + base + vi * 8) = tk_pack8(o);
+    }
+  }
+}
+
+// dx = dsum + rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat))
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(LnParams p) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int vecs = p.c >> 3;
+  const long long base = (long long)row * p.c;
+  const float2 st = *reinterpret_cast<const float2*>(p.stats + 2 * (long long)row);
+  const float mean = st.x, rstd = st.y;
+  float g[NV][8], xh[NV][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+      float gam[8];
+      tk_unpack8(*reinterpret_cast<const uint4*>(p.dy + base + vi * 8), g[i]);
+      tk_unpack8(*reinterpret_cast<const uint4*>(p.x + base + vi * 8), xh[i]);
+      load8f(p.gamma + vi * 8, gam);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = (xh[i][j] - mean) * rstd;
+        g[i][j] *= gam[j];
+        s1 += g[i][j];
+        s2 = fmaf(g[i][j], xh[i][j], s2);
+      }
+    }
+  }
+  const float inv_c = 1.f / (float)p.c;
+  s1 = warp_sum(s1) * inv_c;
+  s2 = warp_sum(s2) * inv_c;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < vecs) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+      if (p.dsum) {
+        float d[8];
+        tk_unpack8(*reinterpret_cast<const uint4*>(p.dsum + base + vi * 8), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += d[j];
+      }
+      *reinterpret_cast<uint4*>(p.dx + base + vi * 8) = tk_pack8(o);
+    }
+  }
+}
+
+
+#define STA_LN_DISPATCH(kernel, nv, grid, stream, p)                             \
+  switch (nv) {                                                                  \
+    case 1: kernel<1><<<grid, kLnWarps * 32, 0, stream>>>(p); break;             \
+    case 2: kernel<2><<<grid, kLnWarps * 32, 0, stream>>>(p); break;             \
+    case 3: kernel<3><<<grid, kLnWarps * 32, 0, stream>>>(p); break;             \
+    case 4: kernel<4><<<grid, kLnWarps * 32, 0, stream>>>(p); break;             \
+    case 5: kernel<5><<<grid, kLnWarps * 32, 0, stream>>>(p); break;             \
+    case 6: kernel<6><<<grid, kLnWarps * 32, 0, stream>>>(p); break;             \
+    case 7: kernel<7><<<grid, kLnWarps * 32, 0, stream>>>(p); break;             \
+    default: kernel<8><<<grid, kLnWarps * 32, 0, stream>>>(p); break;            \
+  }
+
+static int ln_shape_ok(int rows, int channels, const char* who) {
+  if (rows < 1 || channels < 8) return fail(STA_ERR_BAD_ARG, "%s: empty shape (%d x %d)", who, rows, channels);
+  if (channels % 8 != 0 || channels > 2048)
+    return fail(STA_ERR_UNSUPPORTED, "%s: channels %d must be a multiple of 8 and <= 2048", who, channels);
+  return STA_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- GEGLU ---------------------------------------------------------------------------------------------------------
+struct GegluParams {
+  const __half* proj;  // [rows, 2*inner]
+  const __half* dout;  // [rows, inner] (backward)
+  __half* out;         // fwd [rows, inner]; bwd [rows, 2*inner]
+  long long vec_total; // rows * inner / 8
+  int inner_vecs;      // inner / 8
+};
+
+__device__ __forceinline__ float gelu_cdf(float x) { return 0.5f * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(GegluParams p) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.vec_total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / p.inner_vecs;
+    const int vi = (int)(i - row * p.inner_vecs);
+    const __half* pr = p.proj + (row * 2 * p.inner_vecs + vi) * 8;
+    float a[8], g[8];
+    tk_unpack8(*reinterpret_cast<const uint4*>(pr), a);
+    tk_unpack8(*reinterpret_cast<const uint4*>(pr + (long long)p.inner_vecs * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= g[j] * gelu_cdf(g[j]);
+    *reinterpret_cast<uint4*>(p.out + i * 8) = tk_pack8(a);
+  }
+}
+
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(GegluParams p) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.vec_total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / p.inner_vecs;
+    const int vi = (int)(i - row * p.inner_vecs);
+    const long long off = (row * 2 * p.inner_vecs + vi) * 8;
+    float a[8], g[8], d[8], da[8], dg[8];
+    tk_unpack8(*reinterpret_cast<const uint4*>(p.proj + off), a);
+    tk_unpack8(*reinterpret_cast<const uint4*>(p.proj + off + (long long)p.inner_vecs * 8), g);
+    tk_unpack8(*reinterpret_cast<const uint4*>(p.dout + i * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cdf = gelu_cdf(g[j]);
+      const float pdf = 0.3989422804014327f * __expf(-0.5f * g[j] * g[j]);
+      da[j] = d[j] * g[j] * cdf;
+      dg[j] = d[j] * a[j] * fmaf(g[j], pdf, cdf);
+    }
+    *reinterpret_cast<uint4*>(p.out + off) = tk_pack8(da);
+    *reinterpret_cast<uint4*>(p.out + off + (long long)p.inner_vecs * 8) = tk_pack8(dg);
+  }
+}
+
+static int geglu_grid(long long vec_total) {
+  long long blocks = (vec_total + 255) / 256;
+  const long long cap = 148LL * 16;  // grid-stride beyond 16 resident-ish CTAs per SM
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace sta
+
+extern "C" int sta_add_layernorm_fwd(const sta_add_layernorm_args* a, void* stream) {
+  using namespace sta;
+  if (!a || !a->x) return fail(STA_ERR_BAD_ARG, "sta_add_layernorm_fwd: null pointer");
+  int rc = ln_shape_ok(a->rows, a->channels, "sta_add_layernorm_fwd");
+  if (rc) return rc;
+  if (a->gamma && (!a->beta || !a->y)) return fail(STA_ERR_BAD_ARG, "sta_add_layernorm_fwd: gamma without beta / y");
+  if ((a->bias || a->residual) && !a->sum_out && !a->gamma)
+    return fail(STA_ERR_BAD_ARG, "sta_add_layernorm_fwd: nothing to produce");
+  if (!a->gamma && !a->sum_out) return fail(STA_ERR_BAD_ARG, "sta_add_layernorm_fwd: nothing to produce");
+  if (!aligned16(a->x) || !aligned16(a->residual) || !aligned16(a->sum_out) || !aligned16(a->y) || !aligned16(a->bias) ||
+      !aligned16(a->gamma) || !aligned16(a->beta) || (reinterpret_cast<uintptr_t>(a->stats) & 7u))
+    return fail(STA_ERR_BAD_ARG, "sta_add_layernorm_fwd: pointers must be 16-byte aligned");
+  LnParams p{};
+  p.x = reinterpret_cast<const __half*>(a->x);
+  p.bias = a->bias;
+  p.res = reinterpret_cast<const __half*>(a->residual);
+  p.gamma = a->gamma; p.beta = a->beta;
+  p.sum_out = reinterpret_cast<__half*>(a->sum_out);
+  p.y = reinterpret_cast<__half*>(a->y);
+  p.stats = a->stats;
+  p.rows = a->rows; p.c = a->channels; p.eps = a->eps;
+  const int nv = (a->channels / 8 + 31) / 32;
+  const unsigned grid = (unsigned)((a->rows + kLnWarps - 1) / kLnWarps);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  STA_LN_DISPATCH(add_ln_fwd_kernel, nv, grid, s, p);
+  STA_CUDA_CHECK(cudaGetLastError());
+  return STA_OK;
+}
+
+extern "C" int sta_add_layernorm_bwd(const sta_add_layernorm_bwd_args* a, void* stream) {
+  using namespace sta;
+  if (!a || !a->d_y || !a->xs || !a->stats || !a->gamma || !a->d_x)
+    return fail(STA_ERR_BAD_ARG, "sta_add_layernorm_bwd: null pointer");
+  int rc = ln_shape_ok(a->rows, a->channels, "sta_add_layernorm_bwd");
+  if (rc) return rc;
+  if (!aligned16(a->d_y) || !aligned16(a->d_sum) || !aligned16(a->xs) || !aligned16(a->d_x) || !aligned16(a->gamma) ||
+      (reinterpret_cast<uintptr_t>(a->stats) & 7u))
+    return fail(STA_ERR_BAD_ARG, "sta_add_layernorm_bwd: pointers must be 16-byte aligned");
+  LnParams p{};
+  p.dy = reinterpret_cast<const __half*>(a->d_y);
+  p.dsum = reinterpret_cast<const __half*>(a->d_sum);
+  p.x = reinterpret_cast<const __half*>(a->xs);
+  p.stats = const_cast<float*>(a->stats);
+  p.gamma = a->gamma;
+  p.dx = reinterpret_cast<__half*>(a->d_x);
+  p.rows = a->rows; p.c = a->channels;
+  const int nv = (a->channels / 8 + 31) / 32;
+  const unsigned grid = (unsigned)((a->rows + kLnWarps - 1) / kLnWarps);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  STA_LN_DISPATCH(add_ln_bwd_kernel, nv, grid, s, p);
+  STA_CUDA_CHECK(cudaGetLastError());
+  return STA_OK;
+}
+
+static int geglu_check(const sta_geglu_args* a, bool bwd, const char* who) {
+  using namespace sta;
+  if (!a || !a->proj || !a->out || (bwd && !a->d_out)) return fail(STA_ERR_BAD_ARG, "%s: null pointer", who);
+  if (a->rows < 1 || a->inner < 8) return fail(STA_ERR_BAD_ARG, "%s: empty shape", who);
+  if (a->inner % 8 != 0) return fail(STA_ERR_UNSUPPORTED, "%s: inner %d must be a multiple of 8", who, a->inner);
+  if (!aligned16(a->proj) || !aligned16(a->out) || !aligned16(a->d_out))
+    return fail(STA_ERR_BAD_ARG, "%s: pointers must be 16-byte aligned", who);
+  return STA_OK;
+}
+
+extern "C" int sta_geglu_fwd(const sta_geglu_args* a, void* stream) {
+  using namespace sta;
+  int rc = geglu_check(a, false, "sta_geglu_fwd");
+  if (rc) return rc;
+  GegluParams p{};
+  p.proj = reinterpret_cast<const __half*>(a->proj);
+  p.out = reinterpret_cast<__half*>(a->out);
+  p.inner_vecs = a->inner / 8;
+  p.vec_total = (long long)a->rows * p.inner_vecs;
+  geglu_fwd_kernel<<<geglu_grid(p.vec_total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  STA_CUDA_CHECK(cudaGetLastError());
+  return STA_OK;
+}
+
+extern "C" int sta_geglu_bwd(const sta_geglu_args* a, void* stream) {
+  using namespace sta;
+  int rc = geglu_check(a, true, "sta_geglu_bwd");
+  if (rc) return rc;
+  GegluParams p{};
+  p.proj = reinterpret_cast<const __half*>(a->proj);
+  p.dout = reinterpret_cast<const __half*>(a->d_out);
+  p.out = reinterpret_cast<__half*>(a->out);
+  p.inner_vecs = a->inner / 8;
+  p.vec_total = (long long)a->rows * p.inner_vecs;
+  geglu_bwd_kernel<<<geglu_grid(p.vec_total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  STA_CUDA_CHECK(cudaGetLastError());
+  return STA_OK;
+}

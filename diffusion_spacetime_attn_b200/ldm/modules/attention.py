@@ -116,6 +116,48 @@ def _fp16(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == torch.float16 else t.to(torch.float16)
 
 
+def cached_sum(owner: nn.Module, name: str, params, dtype) -> torch.Tensor:
+    """Sum of (frozen) parameters in `dtype`, cached on `owner` and rebuilt only when one of them changed or moved.
+    Used for the fp32 bias / LayerNorm vectors the fused kernels read (no per-evaluation casts inside a CUDA graph)."""
+    params = [p for p in params if p is not None]
+    key = (dtype,) + tuple((p.data_ptr(), p._version, p.device) for p in params)
+    slot = owner.__dict__.setdefault("_sta_cached", {})
+    hit = slot.get(name)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            t = params[0].detach().to(dtype)
+            for p in params[1:]:
+                t = t + p.detach().to(dtype)
+            if t.dim() <= 2:  # conv weights keep their (channels_last) memory format
+                t = t.contiguous()
+        slot[name] = hit = (key, t)
+    return hit[1]
+
+
+def _fused_ok(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float16
+
+
+def _frozen(module: nn.Module) -> bool:
+    """The fused paths read cached, detached copies of the weights (sampling / alpha optimisation: the UNet is frozen,
+    reference ddpm.py:519-523); a module with trainable parameters takes the plain autograd path instead."""
+    if not torch.is_grad_enabled():
+        return True
+    return not any(p.requires_grad for p in module.parameters())
+
+
+def nhwc_tokens(x: torch.Tensor) -> torch.Tensor:
+    """[B, C, H, W] -> [B, H*W, C] ('b c h w -> b (h w) c'); a free view when x is channels_last."""
+    b, c, h, w = x.shape
+    return x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+
+
+def tokens_nhwc(t: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """[B, H*W, C] -> channels_last [B, C, H, W] view ('b (h w) c -> b c h w')."""
+    b, _, c = t.shape
+    return t.reshape(b, h, w, c).permute(0, 3, 1, 2)
+
+
 class CrossAttention(nn.Module):
     """Same parameters as the reference module (to_q / to_k / to_v bias-free, to_out.0 with bias)."""
 
@@ -144,8 +186,7 @@ class CrossAttention(nn.Module):
     def self_attention_core(self, x: torch.Tensor) -> torch.Tensor:
         """softmax(q k^T * scale) v for context = x: one [C, 3C] GEMM, then the flash kernel on strided views."""
         qkv = F.linear(_fp16(x), self._fused_qkv_weight())
-        q, k, v = qkv.chunk(3, dim=-1)
-        return ops.self_attention(q, k, v, self.heads)
+        return ops.self_attention_qkv(qkv, self.heads)  # d(qkv) comes back as ONE buffer (no cat in backward)
 
     def project_out(self, a: torch.Tensor) -> torch.Tensor:
         """to_out on a kernel output (fp16); under autocast the Linear casts itself, otherwise match the weights."""
@@ -299,7 +340,58 @@ class BasicTransformerBlock(nn.Module):
             return _ckpt(self._forward, x, context, coef, use_reentrant=False)
         return self._forward(x, context, coef)
 
+    def _dropout_free(self) -> bool:
+        return not self.training or all(m.p == 0.0 for m in self.modules() if isinstance(m, nn.Dropout))
+
     def _forward(self, x, context=None, coef=None, bboxs_curr_input=None):
+        if _fused_ok(x) and isinstance(self.ff.net[0], GEGLU) and self._dropout_free() and _frozen(self):
+            return self._forward_fused(x, coef)
+        return self._forward_unfused(x, coef)
+
+    def _coef_rows(self, coef, B, n_obj, device):
+        if not n_obj:
+            return None
+        coef_b = coef.reshape(-1, n_obj).to(device=device, dtype=torch.float32)
+        if coef_b.shape[0] != B:
+            coef_b = coef_b.expand(B, n_obj)
+        return coef_b.contiguous()
+
+    def _forward_fused(self, x, coef):
+        """attention.py:268-300 with every elementwise / normalisation step between the GEMMs fused (csrc/sta_tokens.cu):
+        LN1 | QKV GEMM | flash self-attention | to_out GEMM | bias+residual+LN2 | to_q GEMM | fused dual cross-attention |
+        to_out GEMM | bias+residual+LN3 | GEGLU proj GEMM (+bias) | gate | out GEMM | bias+residual.  13 launches."""
+        c = self._cache
+        B, n_obj = c["B"], c["n_obj"]
+        a1, a2, ff = self.attn1, self.attn2, self.ff
+        f32 = torch.float32
+
+        def ln(norm):
+            return cached_sum(self, "g" + str(id(norm)), [norm.weight], f32), cached_sum(self, "b" + str(id(norm)), [norm.bias], f32)
+
+        def w16(lin):
+            return lin.weight if lin.weight.dtype == torch.float16 else cached_sum(self, "w" + str(id(lin)), [lin.weight], torch.float16)
+
+        x = x if x.is_contiguous() else x.contiguous()
+        g1, b1 = ln(self.norm1)
+        g2, b2 = ln(self.norm2)
+        g3, b3 = ln(self.norm3)
+        with torch.autocast("cuda", enabled=False):
+            n1 = ops.layer_norm(x, g1, b1, self.norm1.eps)
+            sa = ops.self_attention_qkv(F.linear(n1, a1._fused_qkv_weight()), a1.heads)
+            t = F.linear(sa, w16(a1.to_out[0]))
+            x1, n2 = ops.add_layer_norm(t, cached_sum(self, "bo1", [a1.to_out[0].bias], f32), x, g2, b2, self.norm2.eps)
+            q = F.linear(n2, w16(a2.to_q))  # computed ONCE (the reference recomputes it 1 + n_obj times)
+            blended = ops.dual_cross_attention(q, c["k"], c["v"], c["masks"], self._coef_rows(coef, B, n_obj, x.device),
+                                               a2.heads)
+            t = F.linear(blended, w16(a2.to_out[0]))
+            x2, n3 = ops.add_layer_norm(t, cached_sum(self, "bo2", [a2.to_out[0].bias], f32), x1, g3, b3, self.norm3.eps)
+            proj, out = ff.net[0].proj, ff.net[2]
+            pb = proj.bias if proj.bias.dtype == torch.float16 else cached_sum(self, "pb", [proj.bias], torch.float16)
+            gated = ops.geglu(F.linear(n3, w16(proj), pb))
+            t = F.linear(gated, w16(out))
+            return ops.bias_residual_add(t, cached_sum(self, "bo3", [out.bias], f32), x2)
+
+    def _forward_unfused(self, x, coef):
         c = self._cache
         B, n_obj = c["B"], c["n_obj"]
         a1 = self.attn1
@@ -332,8 +424,31 @@ class SpatialTransformer(nn.Module):
         )
         self.proj_out = zero_module(nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0))
 
+    def _forward_fused(self, x, context, time, text_index, coef, bboxs_curr):
+        """Same arithmetic with the two 1x1 convolutions as token GEMMs (NHWC memory IS the token matrix): proj_in's
+        bias rides in the GEMM epilogue, proj_out's bias and the `+ x_in` are one fused pass — instead of two
+        broadcast bias kernels (ATen adds the cuDNN conv bias separately) and a residual add."""
+        b, c, h, w = x.shape
+        f32 = torch.float32
+        nw, nb = cached_sum(self, "gn_w", [self.norm.weight], f32), cached_sum(self, "gn_b", [self.norm.bias], f32)
+        x_in = nhwc_tokens(x)
+        x_in = x_in if x_in.is_contiguous() else x_in.contiguous()
+        xn = nhwc_tokens(ops.group_norm_silu(x, nw, nb, self.norm.eps, False))
+        w_in = cached_sum(self, "w_in", [self.proj_in.weight], torch.float16).reshape(self.proj_in.out_channels, c)
+        w_out = cached_sum(self, "w_out", [self.proj_out.weight], torch.float16).reshape(c, -1)
+        with torch.autocast("cuda", enabled=False):
+            t = F.linear(xn, w_in, cached_sum(self, "b_in", [self.proj_in.bias], torch.float16))
+        for block in self.transformer_blocks:
+            t = block(t, context=context, time=time, text_index=text_index, coef=coef, bboxs_curr=bboxs_curr)
+        with torch.autocast("cuda", enabled=False):
+            t = F.linear(_fp16(t), w_out)
+            out = ops.bias_residual_add(t, cached_sum(self, "b_out", [self.proj_out.bias], f32), x_in)
+        return tokens_nhwc(out, h, w)
+
     def forward(self, x, context=None, time=None, text_index=None, coef=None, bboxs_curr=None):
         b, c, h, w = x.shape
+        if _fused_ok(x) and _frozen(self):
+            return self._forward_fused(x, context, time, text_index, coef, bboxs_curr)
         x_in = x
         if x.is_cuda and x.dtype == torch.float16:  # fused NHWC GroupNorm (fp32 statistics), no activation here
             nw = self.norm.weight if self.norm.weight.dtype == torch.float32 else self.norm.weight.float()

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .... import ops as _ops
-from ..attention import BasicTransformerBlock, SpatialTransformer
+from ..attention import BasicTransformerBlock, SpatialTransformer, _frozen, cached_sum, nhwc_tokens, tokens_nhwc
 from .util import checkpoint, conv_nd, linear, normalization, timestep_embedding, zero_module
 
 
@@ -104,7 +104,48 @@ class ResBlock(TimestepBlock):
         flag = self.use_checkpoint and x.shape[-1] * x.shape[-2] >= getattr(self, "checkpoint_min_tokens", 0)
         return checkpoint(self._forward, (x, emb), self.parameters(), flag)
 
+    def _forward_fused(self, x, emb):
+        """openaimodel.py:252-275 for a frozen fp16 NHWC ResBlock.  ATen adds a cuDNN convolution's bias as a separate
+        broadcast kernel, and `h + emb_out[:, :, None, None]` is another one; here the convolutions run bias-free and
+          * conv1's bias + the projected timestep embedding become ONE fp16 [B, C] vector (the embedding GEMM's epilogue
+            adds the conv bias) that the second GroupNorm kernel adds on the fly (sta_groupnorm x_bias),
+          * conv2's bias (+ the 1x1 skip convolution's bias) and the residual add are one fused pass; the 1x1 skip
+            convolution itself is a token GEMM on the NHWC memory."""
+        b, c, hh, ww = x.shape
+        f32, f16 = th.float32, th.float16
+        conv1, conv2, emb_lin = self.in_layers[2], self.out_layers[3], self.emb_layers[1]
+        n1, n2 = self.in_layers[0], self.out_layers[0]
+        g1 = _ops.group_norm_silu(x, cached_sum(self, "g1", [n1.weight], f32), cached_sum(self, "b1", [n1.bias], f32),
+                                  n1.eps, True)
+        with th.autocast("cuda", enabled=False):
+            h = F.conv2d(g1, cached_sum(self, "w1", [conv1.weight], f16), None, conv1.stride, conv1.padding)
+            act = getattr(emb, "_sta_silu", None)  # SiLU(emb) is shared by all 22 ResBlocks (UNetModel.forward)
+            if act is None:
+                act = F.silu(emb)
+            xb = F.linear(act if act.dtype == f16 else act.to(f16), cached_sum(self, "we", [emb_lin.weight], f16),
+                          cached_sum(self, "be", [emb_lin.bias, conv1.bias], f16))
+            g2 = _ops.group_norm_silu(h, cached_sum(self, "g2", [n2.weight], f32), cached_sum(self, "b2", [n2.bias], f32),
+                                      n2.eps, True, x_bias=xb)
+            h = F.conv2d(g2, cached_sum(self, "w2", [conv2.weight], f16), None, conv2.stride, conv2.padding)
+            x_tok = nhwc_tokens(x)
+            if isinstance(self.skip_connection, nn.Identity):
+                skip = x_tok if x_tok.is_contiguous() else x_tok.contiguous()
+                bias = cached_sum(self, "bo", [conv2.bias], f32)
+            else:
+                sk = self.skip_connection
+                skip = F.linear(x_tok, cached_sum(self, "ws", [sk.weight], f16).reshape(sk.out_channels, c))
+                bias = cached_sum(self, "bo", [conv2.bias, sk.bias], f32)
+            out = _ops.bias_residual_add(nhwc_tokens(h), bias, skip)
+        return tokens_nhwc(out, hh, ww)
+
+    def _fusable_block(self, x) -> bool:
+        sk = self.skip_connection
+        return (_fusable(x) and _frozen(self) and (not self.training or self.out_layers[2].p == 0.0)
+                and (isinstance(sk, nn.Identity) or (isinstance(sk, nn.Conv2d) and sk.kernel_size == (1, 1))))
+
     def _forward(self, x, emb):
+        if self._fusable_block(x):
+            return self._forward_fused(x, emb)
         fused = _fusable(x)
         h = self.in_layers[2](gn_silu(self.in_layers[0], x)) if fused else self.in_layers(x)
         emb_out = self.emb_layers(emb).type(h.dtype)
@@ -217,6 +258,8 @@ class UNetModel(nn.Module):
         assert y is None, "SD-v1 is not class-conditional"
         hs = []
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels, repeat_only=False))
+        if not emb.requires_grad:
+            emb._sta_silu = F.silu(emb)  # every ResBlock starts its embedding branch with the same SiLU (:217-223)
         # the reference hands timesteps[0] (a device scalar) to every block, which then syncs on `time == 981`
         # (attention.py:240); callers of this package pass the same value as a host int instead
         time = step_time if step_time is not None else int(timesteps[0].item())  # one sync instead of 16

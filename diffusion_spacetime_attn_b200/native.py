@@ -22,6 +22,10 @@ EXPORTED_SYMBOLS = (
     "sta_xattn_bwd",
     "sta_groupnorm_fwd",
     "sta_groupnorm_bwd",
+    "sta_add_layernorm_fwd",
+    "sta_add_layernorm_bwd",
+    "sta_geglu_fwd",
+    "sta_geglu_bwd",
     "sta_probe_gemm",
     "sta_probe_tmem_bw",
     "sta_debug_read",
@@ -51,7 +55,7 @@ class SattnBwdArgs(C.Structure):
         ("v_token_stride", C.c_int64), ("v_batch_stride", C.c_int64),
         ("o_token_stride", C.c_int64), ("o_batch_stride", C.c_int64),
         ("do_token_stride", C.c_int64), ("do_batch_stride", C.c_int64),
-        ("scale", C.c_float),
+        ("scale", C.c_float), ("dqkv_token_stride", C.c_int64),
     ]
 
 
@@ -84,7 +88,27 @@ class GroupNormArgs(C.Structure):
         ("x", C.c_void_p), ("d_out", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("out", C.c_void_p),
         ("stats", C.c_void_p), ("bwd_stats", C.c_void_p),
         ("batch", C.c_int32), ("hw", C.c_int32), ("channels", C.c_int32), ("silu", C.c_int32), ("eps", C.c_float),
+        ("x_bias", C.c_void_p),
     ]
+
+
+class AddLayerNormArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("sum_out", C.c_void_p), ("y", C.c_void_p), ("stats", C.c_void_p),
+        ("rows", C.c_int32), ("channels", C.c_int32), ("eps", C.c_float),
+    ]
+
+
+class AddLayerNormBwdArgs(C.Structure):
+    _fields_ = [
+        ("d_y", C.c_void_p), ("d_sum", C.c_void_p), ("xs", C.c_void_p), ("stats", C.c_void_p), ("gamma", C.c_void_p),
+        ("d_x", C.c_void_p), ("rows", C.c_int32), ("channels", C.c_int32),
+    ]
+
+
+class GegluArgs(C.Structure):
+    _fields_ = [("proj", C.c_void_p), ("d_out", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int32), ("inner", C.c_int32)]
 
 
 class ProbeArgs(C.Structure):
@@ -121,6 +145,8 @@ def load() -> C.CDLL:
         ("sta_sattn_fwd", SattnFwdArgs), ("sta_sattn_bwd", SattnBwdArgs),
         ("sta_xattn_fwd", XattnFwdArgs), ("sta_xattn_bwd", XattnBwdArgs),
         ("sta_probe_gemm", ProbeArgs), ("sta_groupnorm_fwd", GroupNormArgs), ("sta_groupnorm_bwd", GroupNormArgs),
+        ("sta_add_layernorm_fwd", AddLayerNormArgs), ("sta_add_layernorm_bwd", AddLayerNormBwdArgs),
+        ("sta_geglu_fwd", GegluArgs), ("sta_geglu_bwd", GegluArgs),
     ):
         if not hasattr(lib, name):  # reported by tests/test_cabi.py; calling it raises AttributeError
             continue

@@ -13,7 +13,8 @@ import torch
 from . import native
 
 # number of kernels launched by this module since import (bench.py reports it as `gpu_launches`)
-LAUNCHES = {"sattn_fwd": 0, "sattn_bwd": 0, "xattn_fwd": 0, "xattn_bwd": 0, "groupnorm_fwd": 0, "groupnorm_bwd": 0}
+LAUNCHES = {"sattn_fwd": 0, "sattn_bwd": 0, "xattn_fwd": 0, "xattn_bwd": 0, "groupnorm_fwd": 0, "groupnorm_bwd": 0,
+            "add_layernorm_fwd": 0, "add_layernorm_bwd": 0, "geglu_fwd": 0, "geglu_bwd": 0, "bias_add": 0}
 
 
 def launch_count() -> int:
@@ -198,15 +199,23 @@ def xattn_bwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: O
 
 
 def sattn_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, lse: torch.Tensor,
-              d_out: torch.Tensor, heads: int, scale: Optional[float] = None):
-    """Backward of sattn_fwd: returns (d_q, d_k, d_v) fp16 [b, n, C]."""
+              d_out: torch.Tensor, heads: int, scale: Optional[float] = None,
+              d_fused: Optional[torch.Tensor] = None):
+    """Backward of sattn_fwd: returns (d_q, d_k, d_v) fp16 [b, n, C].  With `d_fused` (a contiguous fp16 [b, n, 3C]
+    buffer) they are written as its three column slices — the gradient of a fused QKV projection, no concatenation."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (d_out, "d_out")):
         _require(t, nm)
     _require(lse, "lse", torch.float32)
     b, n, c = q.shape
     d = c // heads
     scale = float(d ** -0.5) if scale is None else float(scale)
-    d_qkv = torch.empty((3, b, n, c), device=q.device, dtype=torch.float16)
+    if d_fused is not None:
+        _require(d_fused, "d_fused")
+        if tuple(d_fused.shape) != (b, n, 3 * c) or not d_fused.is_contiguous():
+            raise RuntimeError(f"d_fused must be contiguous [{b}, {n}, {3 * c}]")
+        d_qkv = d_fused.view(b, n, 3, c).permute(2, 0, 1, 3)  # [3, b, n, c] views, token stride 3c
+    else:
+        d_qkv = torch.empty((3, b, n, c), device=q.device, dtype=torch.float16)
     dq_accum = torch.empty((b, n, c), device=q.device, dtype=torch.float32)
     delta = torch.empty((b, heads, n), device=q.device, dtype=torch.float32)
     a = native.SattnBwdArgs()
@@ -221,6 +230,7 @@ def sattn_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     a.o_token_stride, a.o_batch_stride = _token_major(out, "out")
     a.do_token_stride, a.do_batch_stride = _token_major(d_out, "d_out")
     a.scale = scale
+    a.dqkv_token_stride = 3 * c if d_fused is not None else 0
     with _timed("sattn_bwd", (b, n, heads, d)):
         native.check(native.load().sta_sattn_bwd(C.byref(a), _stream()), "sta_sattn_bwd")
     LAUNCHES["sattn_bwd"] += 3  # delta, main, dq cast
@@ -273,8 +283,37 @@ class DualCrossAttentionFn(torch.autograd.Function):
         return d_q, None, None, None, d_coef, None
 
 
+class SelfAttentionQKVFn(torch.autograd.Function):
+    """attn1 core on the output of ONE fused [C, 3C] projection: q/k/v are column slices of `qkv` [b, n, 3C], and the
+    backward kernel writes d_q/d_k/d_v straight into one [b, n, 3C] gradient (no split-backward concatenation)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        q, k, v = qkv.chunk(3, dim=-1)
+        need = ctx.needs_input_grad[0]
+        out, lse = sattn_fwd(q, k, v, heads, need_lse=need)
+        if need:
+            ctx.save_for_backward(qkv, out, lse)
+            ctx.heads = heads
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, out, lse = ctx.saved_tensors
+        q, k, v = qkv.chunk(3, dim=-1)
+        if d_out.stride(2) != 1:
+            d_out = d_out.contiguous()
+        d_qkv = torch.empty(qkv.shape, device=qkv.device, dtype=torch.float16)
+        sattn_bwd(q, k, v, out, lse, d_out.to(torch.float16), ctx.heads, d_fused=d_qkv)
+        return d_qkv, None
+
+
 def self_attention(q, k, v, heads):
     return SelfAttentionFn.apply(q, k, v, heads)
+
+
+def self_attention_qkv(qkv, heads):
+    return SelfAttentionQKVFn.apply(qkv, heads)
 
 
 def dual_cross_attention(q, k_ctx, v_ctx, mask, coef, heads):
@@ -289,7 +328,17 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
     return x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
 
 
-def groupnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool):
+def _check_x_bias(x_bias, b: int, c: int):
+    if x_bias is None:
+        return None
+    _require(x_bias, "x_bias")
+    if tuple(x_bias.shape) != (b, c) or not x_bias.is_contiguous():
+        raise RuntimeError(f"x_bias must be a contiguous fp16 [{b}, {c}] tensor, got {tuple(x_bias.shape)}")
+    return x_bias.data_ptr()
+
+
+def groupnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+                  x_bias: Optional[torch.Tensor] = None):
     _require(x, "x")
     _require(gamma, "gamma", torch.float32)
     _require(beta, "beta", torch.float32)
@@ -300,13 +349,14 @@ def groupnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     a = native.GroupNormArgs()
     a.x, a.gamma, a.beta, a.out, a.stats = x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), stats.data_ptr()
     a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
+    a.x_bias = _check_x_bias(x_bias, b, c)
     with _timed("groupnorm_fwd", (b, h * w, c)):
         native.check(native.load().sta_groupnorm_fwd(C.byref(a), _stream()), "sta_groupnorm_fwd")
     LAUNCHES["groupnorm_fwd"] += 2
     return out, stats, x
 
 
-def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool):
+def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool, x_bias: Optional[torch.Tensor] = None):
     b, c, h, w = x.shape
     d_out = _nhwc(d_out if d_out.dtype == torch.float16 else d_out.to(torch.float16))
     d_x = torch.empty_like(x, memory_format=torch.channels_last)
@@ -315,6 +365,7 @@ def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool):
     a.x, a.d_out, a.gamma, a.beta, a.out = x.data_ptr(), d_out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), d_x.data_ptr()
     a.stats, a.bwd_stats = stats.data_ptr(), bstats.data_ptr()
     a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
+    a.x_bias = _check_x_bias(x_bias, b, c)
     with _timed("groupnorm_bwd", (b, h * w, c)):
         native.check(native.load().sta_groupnorm_bwd(C.byref(a), _stream()), "sta_groupnorm_bwd")
     LAUNCHES["groupnorm_bwd"] += 2
@@ -323,19 +374,194 @@ def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool):
 
 class GroupNormSiLUFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, silu):
-        out, stats, x_nhwc = groupnorm_fwd(x, gamma, beta, eps, silu)
+    def forward(ctx, x, gamma, beta, eps, silu, x_bias):
+        out, stats, x_nhwc = groupnorm_fwd(x, gamma, beta, eps, silu, x_bias)
         if ctx.needs_input_grad[0]:
-            ctx.save_for_backward(x_nhwc, gamma, beta, stats)
+            ctx.save_for_backward(x_nhwc, gamma, beta, stats, x_bias)
             ctx.eps, ctx.silu = eps, silu
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        x, gamma, beta, stats = ctx.saved_tensors
-        return groupnorm_bwd(x, d_out, gamma, beta, stats, ctx.eps, ctx.silu), None, None, None, None
+        x, gamma, beta, stats, x_bias = ctx.saved_tensors
+        return groupnorm_bwd(x, d_out, gamma, beta, stats, ctx.eps, ctx.silu, x_bias), None, None, None, None, None
 
 
-def group_norm_silu(x, gamma, beta, eps=1e-5, silu=True):
-    """GroupNorm(32)(x.float()).half() [-> SiLU] in one pass; x fp16 [B, C, H, W] (any layout, NHWC is free)."""
-    return GroupNormSiLUFn.apply(x, gamma, beta, eps, silu)
+def group_norm_silu(x, gamma, beta, eps=1e-5, silu=True, x_bias=None):
+    """GroupNorm(32)((x + x_bias[:, :, None, None]).float()).half() [-> SiLU] in one pass; x fp16 [B, C, H, W] (any
+    layout, NHWC is free); x_bias: optional fp16 [B, C] without gradient (conv bias + timestep embedding)."""
+    if x_bias is not None and x_bias.requires_grad:
+        raise RuntimeError("group_norm_silu: x_bias is treated as a constant (frozen UNet); it must not require grad")
+    return GroupNormSiLUFn.apply(x, gamma, beta, eps, silu, x_bias)
+
+
+# ------------------------------------------------------------------------------------------------------
+# token-major streaming kernels: (bias +) residual add + LayerNorm, GEGLU   (csrc/sta_tokens.cu)
+# ------------------------------------------------------------------------------------------------------
+def _rows2d(t: torch.Tensor, name: str) -> torch.Tensor:
+    """[..., C] fp16 CUDA tensor with dense rows (copies only if it is not already contiguous)."""
+    _require(t, name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def add_layernorm_fwd(x, bias, residual, gamma, beta, eps: float, need_stats: bool = True):
+    """s = x (+ bias) (+ residual); y = LayerNorm(s).  Returns (s, y, stats); s is x itself when nothing is added,
+    y / stats are None when gamma is None (plain fused bias + residual add)."""
+    x = _rows2d(x, "x")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    added = bias is not None or residual is not None
+    if residual is not None:
+        residual = _rows2d(residual, "residual")
+        if residual.shape != x.shape:
+            raise RuntimeError(f"residual {tuple(residual.shape)} must match x {tuple(x.shape)}")
+    for t, nm in ((bias, "bias"), (gamma, "gamma"), (beta, "beta")):
+        if t is not None:
+            _require(t, nm, torch.float32)
+            if t.numel() != c or not t.is_contiguous():
+                raise RuntimeError(f"{nm} must be a contiguous float32 [{c}] tensor")
+    s = torch.empty_like(x) if added else x
+    y = torch.empty_like(x) if gamma is not None else None
+    stats = torch.empty((rows, 2), device=x.device, dtype=torch.float32) if (gamma is not None and need_stats) else None
+    a = native.AddLayerNormArgs()
+    a.x = x.data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.gamma = gamma.data_ptr() if gamma is not None else None
+    a.beta = beta.data_ptr() if gamma is not None else None
+    a.sum_out = s.data_ptr() if added else None
+    a.y = y.data_ptr() if y is not None else None
+    a.stats = stats.data_ptr() if stats is not None else None
+    a.rows, a.channels, a.eps = rows, c, float(eps)
+    with _timed("add_layernorm_fwd", (rows, c)):
+        native.check(native.load().sta_add_layernorm_fwd(C.byref(a), _stream()), "sta_add_layernorm_fwd")
+    LAUNCHES["add_layernorm_fwd"] += 1
+    return s, y, stats
+
+
+def add_layernorm_bwd(d_y, d_sum, xs, stats, gamma):
+    """d_x = d_sum + LN'(d_y) (d_sum may be None)."""
+    d_y = _rows2d(d_y if d_y.dtype == torch.float16 else d_y.to(torch.float16), "d_y")
+    if d_sum is not None:
+        d_sum = _rows2d(d_sum if d_sum.dtype == torch.float16 else d_sum.to(torch.float16), "d_sum")
+    c = xs.shape[-1]
+    rows = xs.numel() // c
+    d_x = torch.empty_like(xs)
+    a = native.AddLayerNormBwdArgs()
+    a.d_y, a.xs, a.stats, a.gamma, a.d_x = d_y.data_ptr(), xs.data_ptr(), stats.data_ptr(), gamma.data_ptr(), d_x.data_ptr()
+    a.d_sum = d_sum.data_ptr() if d_sum is not None else None
+    a.rows, a.channels = rows, c
+    with _timed("add_layernorm_bwd", (rows, c)):
+        native.check(native.load().sta_add_layernorm_bwd(C.byref(a), _stream()), "sta_add_layernorm_bwd")
+    LAUNCHES["add_layernorm_bwd"] += 1
+    return d_x
+
+
+class LayerNormFn(torch.autograd.Function):
+    """y = LayerNorm(x) on fp16 tokens, fp32 statistics / affine, fp16 result (frozen gamma / beta)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        need = ctx.needs_input_grad[0]
+        xs, y, stats = add_layernorm_fwd(x, None, None, gamma, beta, eps, need_stats=need)
+        if need:
+            ctx.save_for_backward(xs, stats, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, d_y):
+        xs, stats, gamma = ctx.saved_tensors
+        return add_layernorm_bwd(d_y, None, xs, stats, gamma), None, None, None
+
+
+class AddLayerNormFn(torch.autograd.Function):
+    """(s, y) = (x + bias + residual, LayerNorm(s)): the residual stream and the next sub-layer's input in one pass.
+    Backward: ONE kernel gives d_s_total = d_s + LN'(d_y), which is the gradient of both x and residual."""
+
+    @staticmethod
+    def forward(ctx, x, bias, residual, gamma, beta, eps):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2]
+        s, y, stats = add_layernorm_fwd(x, bias, residual, gamma, beta, eps, need_stats=need)
+        if need:
+            ctx.save_for_backward(s, stats, gamma)
+        ctx.set_materialize_grads(False)
+        return s, y
+
+    @staticmethod
+    def backward(ctx, d_s, d_y):
+        s, stats, gamma = ctx.saved_tensors
+        if d_y is None:
+            d = d_s
+        else:
+            d = add_layernorm_bwd(d_y, d_s, s, stats, gamma)
+        return (d if ctx.needs_input_grad[0] else None), None, (d if ctx.needs_input_grad[2] else None), None, None, None
+
+
+class BiasResidualAddFn(torch.autograd.Function):
+    """s = x + bias + residual (fp32 accumulate, one rounding); the gradient passes through to x and residual."""
+
+    @staticmethod
+    def forward(ctx, x, bias, residual):
+        s, _, _ = add_layernorm_fwd(x, bias, residual, None, None, 0.0, need_stats=False)
+        return s
+
+    @staticmethod
+    def backward(ctx, d_s):
+        return (d_s if ctx.needs_input_grad[0] else None), None, (d_s if ctx.needs_input_grad[2] else None)
+
+
+def layer_norm(x, gamma, beta, eps=1e-5):
+    return LayerNormFn.apply(x, gamma, beta, eps)
+
+
+def add_layer_norm(x, bias, residual, gamma, beta, eps=1e-5):
+    return AddLayerNormFn.apply(x, bias, residual, gamma, beta, eps)
+
+
+def bias_residual_add(x, bias, residual):
+    return BiasResidualAddFn.apply(x, bias, residual)
+
+
+def geglu_fwd(proj: torch.Tensor) -> torch.Tensor:
+    proj = _rows2d(proj, "proj")
+    inner = proj.shape[-1] // 2
+    rows = proj.numel() // (2 * inner)
+    out = torch.empty(proj.shape[:-1] + (inner,), device=proj.device, dtype=torch.float16)
+    a = native.GegluArgs()
+    a.proj, a.out, a.rows, a.inner = proj.data_ptr(), out.data_ptr(), rows, inner
+    with _timed("geglu_fwd", (rows, inner)):
+        native.check(native.load().sta_geglu_fwd(C.byref(a), _stream()), "sta_geglu_fwd")
+    LAUNCHES["geglu_fwd"] += 1
+    return out
+
+
+def geglu_bwd(proj: torch.Tensor, d_out: torch.Tensor) -> torch.Tensor:
+    d_out = _rows2d(d_out if d_out.dtype == torch.float16 else d_out.to(torch.float16), "d_out")
+    inner = proj.shape[-1] // 2
+    rows = proj.numel() // (2 * inner)
+    d_proj = torch.empty_like(proj)
+    a = native.GegluArgs()
+    a.proj, a.d_out, a.out, a.rows, a.inner = proj.data_ptr(), d_out.data_ptr(), d_proj.data_ptr(), rows, inner
+    with _timed("geglu_bwd", (rows, inner)):
+        native.check(native.load().sta_geglu_bwd(C.byref(a), _stream()), "sta_geglu_bwd")
+    LAUNCHES["geglu_bwd"] += 1
+    return d_proj
+
+
+class GegluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, proj):
+        proj = _rows2d(proj, "proj")
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(proj)
+        return geglu_fwd(proj)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (proj,) = ctx.saved_tensors
+        return geglu_bwd(proj, d_out)
+
+
+def geglu(proj):
+    """value * gelu(gate) of a [.., 2*inner] projection (value | gate), fp16 CUDA."""
+    return GegluFn.apply(proj)

@@ -77,7 +77,7 @@ typedef struct {
   const void* out;   /* forward output, fp16 */
   const void* d_out; /* fp16, same layout as out (do_token_stride / do_batch_stride) */
   const float* lse;  /* from the forward */
-  void* d_q;         /* fp16 [batch, n, heads*head_dim] contiguous */
+  void* d_q;         /* fp16 [batch, n, heads*head_dim], token stride dqkv_token_stride (below) */
   void* d_k;
   void* d_v;
   float* dq_accum; /* workspace, fp32 [batch, n, heads*head_dim]; zeroed by the library */
@@ -89,6 +89,9 @@ typedef struct {
   int64_t o_token_stride, o_batch_stride;
   int64_t do_token_stride, do_batch_stride;
   float scale;
+  /* token stride (elements) shared by d_q / d_k / d_v, batch stride = n * token stride; 0 = dense (heads*head_dim).
+   * 3*heads*head_dim lets the three gradients land in one [batch, n, 3C] buffer = d(fused QKV projection). */
+  int64_t dqkv_token_stride;
 } sta_sattn_bwd_args;
 
 int sta_sattn_bwd(const sta_sattn_bwd_args* args, void* stream);
@@ -161,10 +164,73 @@ typedef struct {
   float* bwd_stats; /* backward only */
   int32_t batch, hw, channels, silu;
   float eps;
+  /* optional fp16 [batch, channels] (dense) added to x BEFORE the statistics (y = GN(x + x_bias)): the ResBlock's
+   * conv bias + projected timestep embedding (openaimodel.py:259-268).  NULL = none.  The backward needs the same
+   * values again (it normalises x + x_bias); no gradient is produced for x_bias. */
+  const void* x_bias;
 } sta_groupnorm_args;
 
 int sta_groupnorm_fwd(const sta_groupnorm_args* args, void* stream);
 int sta_groupnorm_bwd(const sta_groupnorm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused (bias +) residual add + LayerNorm on token-major fp16 activations [rows, channels].
+ * Replaces, inside BasicTransformerBlock._forward (ldm/modules/attention.py:274, 281/297, 299), the chain
+ * `attn(...) + x` -> `norm(x)`: under autocast the reference adds in fp16, copies the sum to fp32, normalises in
+ * fp32 and copies the fp32 result back to fp16 for the next Linear.
+ *   s = x (+ bias) (+ residual)      rounded to fp16 once, written to sum_out
+ *   y = LayerNorm(s) * gamma + beta  fp32 statistics over `channels`, written to y in fp16
+ *   x         fp16 [rows, channels]   a GEMM output without its bias, or the activation itself
+ *   bias      f32  [channels] or NULL;  residual fp16 [rows, channels] or NULL
+ *   gamma, beta f32 [channels]; gamma == NULL: no LayerNorm (only sum_out is produced)
+ *   sum_out   fp16 [rows, channels] or NULL (NULL allowed when there is neither bias nor residual)
+ *   stats     f32  [rows, 2] = (mean, rstd) or NULL (inference)
+ * Backward (weights frozen: d(input) only):  d_x = d_sum + LN'(d_y),  d_sum optional (NULL = 0); `xs` is the
+ * forward's sum_out (or x when nothing was added).  channels: multiple of 8, <= 2048; rows dense (stride = channels).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  const float* bias;
+  const void* residual;
+  const float* gamma;
+  const float* beta;
+  void* sum_out;
+  void* y;
+  float* stats;
+  int32_t rows, channels;
+  float eps;
+} sta_add_layernorm_args;
+
+int sta_add_layernorm_fwd(const sta_add_layernorm_args* args, void* stream);
+
+typedef struct {
+  const void* d_y;   /* fp16 [rows, channels] gradient wrt y */
+  const void* d_sum; /* fp16 [rows, channels] gradient wrt sum_out (the residual path) or NULL */
+  const void* xs;    /* fp16 [rows, channels] the LayerNorm input saved by the forward */
+  const float* stats;
+  const float* gamma;
+  void* d_x; /* fp16 [rows, channels] */
+  int32_t rows, channels;
+} sta_add_layernorm_bwd_args;
+
+int sta_add_layernorm_bwd(const sta_add_layernorm_bwd_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * GEGLU gate (ldm/modules/attention.py:42-49: `x, gate = proj(x).chunk(2, -1); x * F.gelu(gate)`, exact erf GELU).
+ *   proj   fp16 [rows, 2*inner]   (value | gate) halves of GEGLU.proj's output
+ *   fwd:   out fp16 [rows, inner]    = value * gelu(gate)
+ *   bwd:   d_out fp16 [rows, inner] -> out fp16 [rows, 2*inner] = d(proj)   (d value | d gate)
+ * inner: multiple of 8.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* proj;
+  const void* d_out; /* backward only */
+  void* out;
+  int32_t rows, inner;
+} sta_geglu_args;
+
+int sta_geglu_fwd(const sta_geglu_args* args, void* stream);
+int sta_geglu_bwd(const sta_geglu_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Test hook: one tcgen05 GEMM tile with caller-supplied UMMA descriptors (tests/test_probe_gpu.py pins the
