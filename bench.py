@@ -382,7 +382,9 @@ def run_native(args):
                                    "alpha inner-opt on (%d epochs), batch=1 per GPU" % (args.ddim_steps, args.epochs),
                        "weights": pipe.weights, "prompts": "synthetic_gpt.txt (gpt.txt record format)",
                        "l2": "inputs larger than L2: each step streams ~3.4 GB of weights 300+ times",
-                       "execution": ("CUDA graphs per UNet evaluation (fwd graph + recompute/bwd graph), fp16 weights"
+                       "execution": ("CUDA graphs per UNet evaluation, fp16 weights; differentiable evaluations keep their "
+                                     "activations in HBM slots (fwd-with-grad graph + bwd graph per slot), recompute graph "
+                                     "when no slot is free: %s" % json.dumps(runner.slot_summary())
                                      if pipe.cuda_graphs else "eager, block-level gradient checkpointing"),
                        "parallelism": "dp%d (prompt-sharded, weights broadcast once: %d bytes)" % (world, bcast_bytes)},
             "e2e": {"value": n_img / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -16,21 +16,50 @@ launch (the C ABI enqueues on the current stream, allocates nothing and never sy
 
 Static state: inputs are copied into fixed buffers before a replay; the per-prompt attention caches (projected context
 K/V, masks) are fixed buffers too, refreshed in place by BasicTransformerBlock._build_cache.
+
+Activation slots (180 GB of HBM instead of recompute).  The reference checkpoints every block because 51 differentiable
+evaluations do not fit its 48 GB cards (util.py:102-148); one evaluation's saved activations are ~1.5 GB
+here, so a B200 can simply KEEP them.  A slot is a pair of graphs sharing one private memory pool:
+
+  slot.g_fwd   forward WITH autograd recording — the saved activations stay in the slot's pool after the replay
+  slot.g_bwd   backward only — reads them back; replayed (once) when autograd reaches this evaluation
+
+Evaluation i of a trajectory takes a free slot in its forward and releases it in its backward; when all slots are
+taken (or the memory budget is reached) it falls back to the recompute graph above, so any mix is exact.  Slots of
+different (batch, n_obj) signatures share their pools pairwise (slot k of every signature captures into pool k):
+prompts run one after the other, so their activations are never alive at the same time.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+import os
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
 from . import ops
 
 
+class _Slot:
+    """One retained evaluation: forward-with-grad graph + backward graph over a shared private pool."""
+
+    __slots__ = ("g_fwd", "g_bwd", "eps", "dx", "dcoef", "busy", "launches_fwd", "launches_bwd", "trace_fwd", "trace_bwd")
+
+    def __init__(self):
+        self.busy = False
+
+
 class GraphedUNetEval:
     """Captured graphs of `unet` for a fixed (batch, n_obj, latent) signature."""
 
-    def __init__(self, unet, batch2: int, n_obj: int, latent_hw: Tuple[int, int], ctx_shape=(77, 768), warmup: int = 2):
+    def __init__(self, unet, batch2: int, n_obj: int, latent_hw: Tuple[int, int], ctx_shape=(77, 768), warmup: int = 2,
+                 pools: Optional[list] = None, max_slots: int = 0, reserve_bytes: int = 24 << 30):
         self.unet = unet
+        self.pools = pools if pools is not None else []   # shared with the other signatures of the runner
+        self.max_slots = max_slots
+        self.reserve_bytes = reserve_bytes
+        self.slots: List[_Slot] = []
+        self.slot_bytes = 0
+        self.slot_replays_fwd = self.slot_replays_bwd = 0
         dev = next(unet.parameters()).device
         h, w = latent_hw
         B = batch2 // 2
@@ -99,6 +128,86 @@ class GraphedUNetEval:
         self.trace_bwd = ops.trace_stop()
         torch.cuda.synchronize()
 
+    # -- activation slots ----------------------------------------------------------------------------
+    def _capture_slot(self) -> Optional[_Slot]:
+        """Capture one more (forward-with-grad, backward) graph pair into pool len(self.slots); None if out of budget."""
+        k = len(self.slots)
+        if k >= self.max_slots:
+            return None
+        free, _ = torch.cuda.mem_get_info()
+        need = self.slot_bytes if self.slot_bytes else (4 << 30)
+        if k >= len(self.pools) and free < self.reserve_bytes + need:  # a NEW pool would not fit next to the VAE / CLIP pass
+            self.max_slots = k
+            return None
+        if k >= len(self.pools):
+            self.pools.append(torch.cuda.graph_pool_handle())
+        pool = self.pools[k]
+        slot = _Slot()
+        torch.cuda.synchronize()
+        before = torch.cuda.memory_reserved()
+        with torch.enable_grad():
+            xg = self.x.detach().requires_grad_(True)   # views of the static input buffers
+            cg = self.coef.detach().requires_grad_(True)
+            n0 = ops.launch_count()
+            ops.trace_start()
+            slot.g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(slot.g_fwd, pool=pool):
+                eps = self._eval(xg, cg)
+            slot.launches_fwd = ops.launch_count() - n0
+            slot.trace_fwd = ops.trace_stop()
+            n0 = ops.launch_count()
+            ops.trace_start()
+            slot.g_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(slot.g_bwd, pool=pool):
+                grads = torch.autograd.grad(eps, [xg] + ([cg] if self.n_obj else []), self.d_eps)
+            slot.launches_bwd = ops.launch_count() - n0
+            slot.trace_bwd = ops.trace_stop()
+        slot.eps, slot.dx = eps.detach(), grads[0]
+        slot.dcoef = grads[1] if self.n_obj else None
+        torch.cuda.synchronize()
+        if not self.slot_bytes:
+            self.slot_bytes = max(torch.cuda.memory_reserved() - before, 1 << 20)
+        self.slots.append(slot)
+        return slot
+
+    def acquire_slot(self) -> Optional[_Slot]:
+        for s in self.slots:
+            if not s.busy:
+                s.busy = True
+                return s
+        s = self._capture_slot()
+        if s is not None:
+            s.busy = True
+        return s
+
+    def release_all(self) -> None:
+        for s in self.slots:
+            s.busy = False
+
+    def forward_keep(self, slot: _Slot, x, t, coef) -> torch.Tensor:
+        """Forward of one evaluation whose activations stay in `slot` until backward_kept()."""
+        self.x.copy_(x)
+        self.t.copy_(t)
+        if self.n_obj:
+            self.coef.copy_(coef.reshape(self.B, self.n_obj))
+        slot.g_fwd.replay()
+        self.slot_replays_fwd += 1
+        ops.LAUNCHES["graph_replayed"] = ops.LAUNCHES.get("graph_replayed", 0) + slot.launches_fwd
+        return slot.eps.clone()
+
+    def backward_kept(self, slot: _Slot, coef, d_eps):
+        if not slot.busy:
+            raise RuntimeError("this evaluation's activation slot was already consumed (backward twice?)")
+        if self.n_obj:  # the fused cross-attention saved the static coef buffer itself: restore this evaluation's values
+            self.coef.copy_(coef.reshape(self.B, self.n_obj))
+        self.d_eps.copy_(d_eps)
+        slot.g_bwd.replay()
+        self.slot_replays_bwd += 1
+        ops.LAUNCHES["graph_replayed"] = ops.LAUNCHES.get("graph_replayed", 0) + slot.launches_bwd
+        out = slot.dx.clone(), (slot.dcoef.clone() if self.n_obj else None)
+        slot.busy = False
+        return out
+
     # ------------------------------------------------------------------------------------------------
     def set_context(self, context: torch.Tensor) -> None:
         self.context.copy_(context)
@@ -131,12 +240,18 @@ class _GraphedEvalFn(torch.autograd.Function):
         ctx.runner = runner
         ctx.has_coef = coef is not None
         ctx.save_for_backward(x, t, coef if coef is not None else x.new_zeros(0))
+        ctx.slot = runner.acquire_slot() if any(ctx.needs_input_grad[:2]) else None
+        if ctx.slot is not None:
+            return runner.forward_keep(ctx.slot, x, t, coef)
         return runner.forward(x, t, coef)
 
     @staticmethod
     def backward(ctx, d_eps):
         x, t, coef = ctx.saved_tensors
-        dx, dcoef = ctx.runner.backward(x, t, coef if ctx.has_coef else None, d_eps)
+        if ctx.slot is not None:
+            dx, dcoef = ctx.runner.backward_kept(ctx.slot, coef if ctx.has_coef else None, d_eps)
+        else:
+            dx, dcoef = ctx.runner.backward(x, t, coef if ctx.has_coef else None, d_eps)
         if ctx.has_coef and dcoef is not None:
             dcoef = dcoef.reshape(coef.shape)
         return dx, (dcoef if ctx.has_coef else None), None, None
@@ -145,10 +260,15 @@ class _GraphedEvalFn(torch.autograd.Function):
 class GraphedModelRunner:
     """Keeps one GraphedUNetEval per (batch, n_obj, latent) signature and routes apply_model_extra through it."""
 
-    def __init__(self, unet):
+    def __init__(self, unet, max_slots: Optional[int] = None, reserve_gib: Optional[float] = None):
         self.unet = unet
         self.graphs: Dict[tuple, GraphedUNetEval] = {}
         self.active: Optional[GraphedUNetEval] = None
+        # activation slots: at most `max_slots` retained evaluations per trajectory (0 = always recompute), never
+        # eating into `reserve_gib` of free HBM (VAE decode + CLIP loss backward, allocator slack)
+        self.max_slots = int(os.environ.get("STA_MAX_SLOTS", "64")) if max_slots is None else int(max_slots)
+        self.reserve_bytes = int(float(os.environ.get("STA_SLOT_RESERVE_GIB", "24") if reserve_gib is None else reserve_gib) * 2 ** 30)
+        self.pools: list = []
 
     def begin_prompt(self, x_shape, context, local_contexts, bboxes, first_timestep: int) -> None:
         """Refresh the static per-prompt state (context K/V caches, masks) and select / capture the graph."""
@@ -160,7 +280,8 @@ class GraphedModelRunner:
         g = self.graphs.get(key)
         fresh = g is None
         if fresh:
-            g = GraphedUNetEval(unet, batch2, n_obj, (x_shape[2], x_shape[3]), tuple(context.shape[1:]))
+            g = GraphedUNetEval(unet, batch2, n_obj, (x_shape[2], x_shape[3]), tuple(context.shape[1:]), pools=self.pools,
+                                max_slots=self.max_slots, reserve_bytes=self.reserve_bytes)
         g.set_context(context)
         g.bboxes = bboxes
         # (re)build every block's cache in place from the new context / local embeddings / layout
@@ -170,6 +291,7 @@ class GraphedModelRunner:
         if fresh:
             g.capture(bboxes)
             self.graphs[key] = g
+        g.release_all()  # slots of an abandoned trajectory (exception, no backward) become free again
         self.active = g
 
     def __call__(self, x_in, t_in, coef):
@@ -179,11 +301,22 @@ class GraphedModelRunner:
         """{(kind, geometry): launches} of the sta_* kernels replayed so far (all signatures)."""
         hist = {}
         for g in self.graphs.values():
-            for trace, n in ((g.trace_fwd, g.replays_fwd), (g.trace_bwd, g.replays_bwd)):
+            pairs = [(g.trace_fwd, g.replays_fwd), (g.trace_bwd, g.replays_bwd)]
+            if g.slots:  # every slot holds the same two launch sequences
+                pairs += [(g.slots[0].trace_fwd, g.slot_replays_fwd), (g.slots[0].trace_bwd, g.slot_replays_bwd)]
+            for trace, n in pairs:
                 for kk in trace:
                     hist[kk] = hist.get(kk, 0) + n
         return hist
 
     def reset_counters(self):
         for g in self.graphs.values():
-            g.replays_fwd = g.replays_bwd = 0
+            g.replays_fwd = g.replays_bwd = g.slot_replays_fwd = g.slot_replays_bwd = 0
+
+    def new_trajectory(self) -> None:
+        """Called by the samplers before each differentiable trajectory: all activation slots are free again."""
+        if self.active is not None:
+            self.active.release_all()
+
+    def slot_summary(self) -> dict:
+        return {str(k): {"slots": len(g.slots), "slot_gib": round(g.slot_bytes / 2 ** 30, 3)} for k, g in self.graphs.items()}

@@ -168,6 +168,8 @@ class PLMSSampler(object):
         epochs = self.num_epochs if do_opt else 1
         losses, img, decoded = [], None, None
         for epoch in range(epochs):
+            if runner is not None:
+                runner.new_trajectory()
             with torch.set_grad_enabled(do_opt):
                 img = self._trajectory(img_input.clone(), cond, unconditional_conditioning,
                                        unconditional_guidance_scale, W if n_obj else None, bboxes_arg, text_index)

@@ -193,18 +193,20 @@ def test_cuda_graph_execution_matches_eager_alpha_optimisation():
     G = torch.randn(1, 4, lat, lat, generator=g).cuda()
     loss_fn = lambda imgs, *a: ((imgs.float() * G).sum(), [(imgs.float() * G).sum()])
     results = {}
-    for mode in ("eager", "graph"):
+    # graph: activation slots for every evaluation; graph_mixed: 2 slots, the other 3 evaluations recompute;
+    # graph_recompute: no slots (evaluation-level recompute only)
+    for mode in ("eager", "graph", "graph_mixed", "graph_recompute"):
         m, sd, cfg = _tiny_models(5)
         ld = LatentDiffusion(unet_config={"params": dict(TINY)}, build_first_stage=False)
         ld.model.diffusion_model = m
         ld = ld.cuda().eval().requires_grad_(False)
-        if mode == "graph":
+        if mode.startswith("graph"):
             m.half()
             for mod in m.modules():
                 if isinstance(mod, (torch.nn.GroupNorm, torch.nn.LayerNorm)):
                     mod.float()
             m.set_checkpointing(False)
-            ld.graph_runner = GraphedModelRunner(m)
+            ld.graph_runner = GraphedModelRunner(m, max_slots={"graph": 64, "graph_mixed": 2, "graph_recompute": 0}[mode])
         else:
             m.set_checkpointing(True)
         sampler = PLMSSampler(ld, clip_loss_model=torch.nn.Identity(), save_images=False, num_epochs=2, lr=0.05,
@@ -221,15 +223,25 @@ def test_cuda_graph_execution_matches_eager_alpha_optimisation():
             outs.append((sampler.last_result["latent"].float().cpu(), sampler.last_result["weighting_parameter"].cpu(),
                          sampler.last_result["losses"]))
         results[mode] = outs
-        if mode == "graph":
+        if mode.startswith("graph"):
             assert len(ld.graph_runner.graphs) == 1, "the second prompt must reuse the captured graphs"
+            ge = next(iter(ld.graph_runner.graphs.values()))
+            want = {"graph": S + 1, "graph_mixed": 2, "graph_recompute": 0}[mode]
+            assert len(ge.slots) == want, (mode, len(ge.slots))
+            assert not any(sl.busy for sl in ge.slots), "every slot must be released by its backward"
+            kept, recomputed = ge.slot_replays_bwd, ge.replays_bwd
+            assert kept == 2 * 2 * want and kept + recomputed == 2 * 2 * (S + 1), (mode, kept, recomputed)
     torch.cuda.synchronize()
     assert native.device_error() == 0
-    for (z_e, w_e, l_e), (z_g, w_g, l_g) in zip(results["eager"], results["graph"]):
-        assert rel_l2(z_g, z_e) < 1e-2
-        dw_e = w_e - 2.5  # the Adam updates (initial value 5 / n_obj = 2.5)
-        assert (w_g - w_e).abs().max().item() < 0.1 * dw_e.abs().max().item() + 1e-4
-        assert abs(l_g[0][0] - l_e[0][0]) < 2e-2 * abs(l_e[0][0]) + 1e-2
+    for mode in ("graph", "graph_mixed", "graph_recompute"):
+        for (z_e, w_e, l_e), (z_g, w_g, l_g) in zip(results["eager"], results[mode]):
+            assert rel_l2(z_g, z_e) < 1e-2, mode
+            dw_e = w_e - 2.5  # the Adam updates (initial value 5 / n_obj = 2.5)
+            assert (w_g - w_e).abs().max().item() < 0.1 * dw_e.abs().max().item() + 1e-4, mode
+            assert abs(l_g[0][0] - l_e[0][0]) < 2e-2 * abs(l_e[0][0]) + 1e-2, mode
+    # kept activations vs recomputed ones: the same kernels on the same data -> the same optimised weights
+    for (z_a, w_a, _), (z_b, w_b, _) in zip(results["graph"], results["graph_recompute"]):
+        assert (w_a - w_b).abs().max().item() < 2e-3 and rel_l2(z_a, z_b) < 2e-3
     assert (results["graph"][0][0] - results["graph"][1][0]).abs().max() > 1e-2  # different prompts, different latents
 
 

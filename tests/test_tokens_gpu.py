@@ -168,5 +168,3 @@ def test_self_attention_fused_qkv_gradient_layout(b, n, h, d):
     # dq is accumulated with fp32 reduce-adds whose order differs from launch to launch: compare with a tolerance
     diff = (a.grad.float() - bq.grad.float()).abs().max().item()
     assert diff <= 2e-3 * bq.grad.float().abs().max().item(), diff
-    c3 = 3 * c
-    assert torch.equal(a.grad.view(b, n, 3, c)[:, :, 1:], bq.grad.view(b, n, 3, c)[:, :, 1:]) or diff < 1e-4 or c3  # dk/dv: same
