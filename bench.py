@@ -136,7 +136,8 @@ def launch_bytes(kind, key):
 
 def standalone_kernel_ms(kind, key, iters=10):
     """Mean device time of ONE launch of a sta_* kernel at the step's exact geometry: `iters` back-to-back launches
-    between two CUDA events on the launching stream, after a warm-up, with an L2 flush (256 MiB memset) before."""
+    (one CUDA graph) between two CUDA events on the launching stream, after a warm-up, with an L2 flush (256 MiB
+    memset) before."""
     import torch
 
     from diffusion_spacetime_attn_b200 import ops
@@ -174,11 +175,17 @@ def standalone_kernel_ms(kind, key, iters=10):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(3):
         fn()
+    # the launches are captured into one CUDA graph (as they run inside the step) so that the host launch rate of
+    # this Python process is not part of the measurement (it dominated the small streaming kernels)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(iters):
+            fn()
+    graph.replay()
     flush.zero_()
     a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(iters):
-        fn()
+    graph.replay()
     b_.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b_) / iters
@@ -313,6 +320,7 @@ def run_native(args):
     dev_ms = ev0.elapsed_time(ev1)
     launches = ops.launch_count() - launches0
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+    reserved_mem = torch.cuda.memory_reserved() / 2 ** 30  # includes the graphs' private pools (activation slots)
 
     # ---- timed region 2: end to end through the public API with host buffers ----
     idx2 = list(range(args.warmup + args.steps, args.warmup + 2 * args.steps))
@@ -394,6 +402,7 @@ def run_native(args):
             "roofline": roofline,
             "kernels": kernels[:8],
             "peak_mem_gib": peak_mem,
+            "reserved_mem_gib": reserved_mem,
             "device_error": err,
         }
         if world == 1 and not args.no_cpu_baseline:

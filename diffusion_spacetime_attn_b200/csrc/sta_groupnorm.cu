@@ -15,6 +15,8 @@
 #include "../../include/sta_b200.h"
 #include "sta_common.cuh"
 #include "sta_host.h"
+#include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace sta {
 
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(GnParams p) {
 
 // per-thread constants of the 8 channels it owns
 struct GnChan {
-  float mean[8], rstd[8], gam[8], bet[8], xb[8];
+  float rstd[8], shx[8], gam[8], bet[8];  // xhat = x * rstd + shx,  shx = (x_bias - mean) * rstd
 };
 
 __device__ __forceinline__ void gn_load_chan(const GnParams& p, const GnMap& m, int b, GnChan& k) {
@@ -166,15 +168,15 @@ __device__ __forceinline__ void gn_load_chan(const GnParams& p, const GnMap& m, 
   load8(p.gamma + m.c0, k.gam);
   load8(p.beta + m.c0, k.bet);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) k.xb[i] = 0.f;
-  if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.c + m.c0), k.xb);
+  for (int i = 0; i < 8; ++i) k.shx[i] = 0.f;
+  if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.c + m.c0), k.shx);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (m.c0 + i) / cg;
     const float mean = p.stats[(b * kGnGroups + g) * 2] * inv_n;
     const float var = fmaxf(p.stats[(b * kGnGroups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-    k.mean[i] = mean;
     k.rstd[i] = rsqrtf(var + p.eps);
+    k.shx[i] = (k.shx[i] - mean) * k.rstd[i];
   }
 }
 
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(GnParams p) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     sc[i] = k.rstd[i] * k.gam[i];
-    sh[i] = fmaf(k.xb[i] - k.mean[i], sc[i], k.bet[i]);
+    sh[i] = fmaf(k.shx[i], k.gam[i], k.bet[i]);
   }
   const int r0 = blockIdx.x * p.rows_per_block, r1 = min(p.hw, r0 + p.rows_per_block);
   const long long off = ((long long)b * p.hw) * p.c + m.c0;
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(GnParams p) {
 }
 
 // ---- backward pass 1: per (b, group) sum(dxhat) and sum(dxhat * xhat), dxhat = dy * silu'(z) * gamma ----------------
+template <bool SILU>
 __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_stats_kernel(GnParams p) {
   extern __shared__ float gn_smem[];
   float* part_1 = gn_smem;
@@ -249,9 +252,9 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_stats_kernel(GnParams p)
           unpack8(vd[u], d);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float xh = (f[i] + k.xb[i] - k.mean[i]) * k.rstd[i];
+            const float xh = fmaf(f[i], k.rstd[i], k.shx[i]);
             float dz = d[i];
-            if (p.silu) dz *= dsilu_f(fmaf(xh, k.gam[i], k.bet[i]));
+            if (SILU) dz *= dsilu_f(fmaf(xh, k.gam[i], k.bet[i]));
             const float dxh = dz * k.gam[i];
             a1[i] += dxh;
             a2[i] = fmaf(dxh, xh, a2[i]);
@@ -264,6 +267,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_stats_kernel(GnParams p)
 }
 
 // ---- backward pass 2: dx = rstd * (dxhat - mean_g(dxhat) - xhat * mean_g(dxhat * xhat)) ---------------------------
+template <bool SILU>
 __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_apply_kernel(GnParams p) {
   const GnMap m(p.c, p.lanes);
   const int b = blockIdx.y, cg = p.c / kGnGroups;
@@ -300,9 +304,9 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_apply_kernel(GnParams p)
         unpack8(vd[u], d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float xh = (f[i] + k.xb[i] - k.mean[i]) * k.rstd[i];
+          const float xh = fmaf(f[i], k.rstd[i], k.shx[i]);
           float dz = d[i];
-          if (p.silu) dz *= dsilu_f(fmaf(xh, k.gam[i], k.bet[i]));
+          if (SILU) dz *= dsilu_f(fmaf(xh, k.gam[i], k.bet[i]));
           f[i] = k.rstd[i] * (dz * k.gam[i] - m1[i] - xh * m2[i]);
         }
         *reinterpret_cast<uint4*>(p.out + off + (long long)rr * p.c) = pack8(f);
@@ -337,6 +341,332 @@ static int gn_launch_shape(const sta_groupnorm_args* a, GnLaunch* L) {
   return STA_OK;
 }
 
+// =====================================================================================================================
+// Single-launch kernels on thread-block clusters.  A cluster owns (sample b, a chunk of 1-4 whole groups whose channels
+// form whole 16-byte vectors); its CTAs split the rows, every thread keeps its rows in REGISTERS, the per-group sums are
+// reduced warp -> CTA (shared memory) -> cluster (distributed shared memory), and the normalisation is applied to the
+// registers: ONE launch, the activation is read once, no global atomics and no memset node.  In a captured UNet
+// evaluation the two-pass path costs ~12 us per GroupNorm of pure node overhead (memset + 2 dependent kernels); the
+// tensors are 1-16 MB, so this matters more than the bytes.  Shapes that do not fit the register budget (the 512^2 VAE
+// feature maps, 960 channels at 64^2) take the two-pass kernels above.
+// =====================================================================================================================
+struct GnClusterParams {
+  const __half* x;
+  const __half* dy;
+  const __half* xb;
+  const float* gamma;
+  const float* beta;
+  __half* out;
+  float* stats;   // [B, 32, 2] raw sums of the forward (written by the forward kernel, read by the backward kernel)
+  float* bstats;  // backward: [B, 32, 2] written for completeness (same meaning as the two-pass kernels)
+  int hw, c, cg;
+  int chunk_c;       // channels per cluster: gc groups, a multiple of 8
+  int gc;            // groups per cluster
+  int vpr;           // 16-byte vectors per row of the chunk
+  int lanes;         // row lanes per CTA
+  int rows_per_cta;
+  int silu;
+  float eps;
+};
+
+// per-CTA sums of the thread partials a[8], b[8] (8 channels of ONE vector column j) -> red[2*g + {0,1}] for the chunk's
+// groups.  A vector spans at most two groups (cg >= 8): each thread first folds its 8 channels into (lo, hi) group
+// partials — one float4 in shared memory per thread — then warp g sums the entries that touch group g.
+__device__ __forceinline__ void gn_cta_group_sums(float* part, float* red, const float* a, const float* b, bool active,
+                                                  int lane_row, int j, const GnClusterParams& p) {
+  float4* part4 = reinterpret_cast<float4*>(part);
+  {
+    const int gl0 = (j * 8) / p.cg;
+    const int nb = min(8, (gl0 + 1) * p.cg - j * 8);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);  // (a_lo, b_lo, a_hi, b_hi)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < nb) { v.x += a[i]; v.y += b[i]; }
+      else { v.z += a[i]; v.w += b[i]; }
+    }
+    if (active) part4[lane_row * p.vpr + j] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < p.gc; g += nwarps) {
+    const int j_lo = (g * p.cg) / 8, j_hi = ((g + 1) * p.cg - 1) / 8;  // vector columns touching group g
+    float sa = 0.f, sb = 0.f;
+    for (int lr = lane; lr < p.lanes; lr += 32) {
+      for (int jj = j_lo; jj <= j_hi; ++jj) {
+        const float4 v = part4[lr * p.vpr + jj];
+        const bool is_lo = (jj * 8) / p.cg == g;
+        sa += is_lo ? v.x : v.z;
+        sb += is_lo ? v.y : v.w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if (lane == 0) { red[2 * g] = sa; red[2 * g + 1] = sb; }
+  }
+}
+
+// cluster-wide totals of red[0 .. 2*gc) -> tot[0 .. 2*gc) in every CTA's shared memory
+__device__ __forceinline__ void gn_cluster_totals(float* red, float* tot, int n_vals) {
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cluster = cgx::this_cluster();
+  cluster.sync();  // every CTA's red[] is written
+  if ((int)threadIdx.x < n_vals) {
+    float acc = 0.f;
+    const unsigned cs = cluster.num_blocks();
+    for (unsigned r = 0; r < cs; ++r) acc += cluster.map_shared_rank(red, r)[threadIdx.x];
+    tot[threadIdx.x] = acc;
+  }
+  cluster.sync();  // totals visible locally; no CTA may exit (or reuse red[]) while a peer still reads it
+}
+
+template <int R>
+__global__ void __launch_bounds__(352) gn_cluster_fwd_kernel(GnClusterParams p) {
+  extern __shared__ float gn_smem[];
+  __shared__ float red[8], tot[8];
+  const int j = threadIdx.x % p.vpr, lane_row = threadIdx.x / p.vpr;
+  const bool active = lane_row < p.lanes;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int ch0 = chunk * p.chunk_c + j * 8;
+  const int r0 = blockIdx.x * p.rows_per_cta, r1 = min(p.hw, r0 + p.rows_per_cta);
+  const long long off = ((long long)b * p.hw) * p.c + ch0;
+  uint4 v[R];
+  float xb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+      if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.c + ch0), xb);
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const int rr = r0 + lane_row + u * p.lanes;
+        if (rr < r1) v[u] = *reinterpret_cast<const uint4*>(p.x + off + (long long)rr * p.c);
+      }
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        if (r0 + lane_row + u * p.lanes < r1) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float t = f[i] + xb[i];
+            s[i] += t;
+            q[i] = fmaf(t, t, q[i]);
+          }
+        }
+      }
+    }
+    gn_cta_group_sums(gn_smem, red, s, q, active, lane_row, j, p);
+  }
+  gn_cluster_totals(red, tot, 2 * p.gc);
+  const int g0 = chunk * p.gc;
+  if (blockIdx.x == 0 && (int)threadIdx.x < 2 * p.gc)  // raw sums for the backward (same layout as the two-pass path)
+    p.stats[((long long)b * kGnGroups + g0) * 2 + threadIdx.x] = tot[threadIdx.x];
+  if (!active) return;
+  const float inv_n = 1.f / ((float)p.hw * (float)p.cg);
+  float sc[8], sh[8], gam[8], bet[8];
+  load8(p.gamma + ch0, gam);
+  load8(p.beta + ch0, bet);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gl = (j * 8 + i) / p.cg;  // group within the chunk
+    const float mean = tot[2 * gl] * inv_n;
+    const float var = fmaxf(tot[2 * gl + 1] * inv_n - mean * mean, 0.f);
+    sc[i] = rsqrtf(var + p.eps) * gam[i];
+    sh[i] = fmaf(xb[i] - mean, sc[i], bet[i]);
+  }
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const int rr = r0 + lane_row + u * p.lanes;
+    if (rr < r1) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = fmaf(f[i], sc[i], sh[i]);
+        f[i] = p.silu ? silu_f(z) : z;
+      }
+      *reinterpret_cast<uint4*>(p.out + off + (long long)rr * p.c) = pack8(f);
+    }
+  }
+}
+
+// Backward.  The kernel is instruction-bound, not bandwidth-bound (the first version spent 89 thread-instructions per
+// element, mostly evaluating silu' twice): phase 1 turns each (x, dy) pair into (xhat, dxhat = dy * silu'(z) * gamma),
+// accumulates the two group sums and keeps the pair as packed fp16 IN PLACE of the raw data; phase 2 is three FMAs per
+// element.  fp16 rounding of xhat / dxhat (2^-11 relative) is below the rounding of the fp16 result itself.
+template <int R, bool SILU>
+__global__ void __launch_bounds__(640) gn_cluster_bwd_kernel(GnClusterParams p) {
+  extern __shared__ float gn_smem[];
+  __shared__ float red[8], tot[8];
+  const int j = threadIdx.x % p.vpr, lane_row = threadIdx.x / p.vpr;
+  const bool active = lane_row < p.lanes;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  const int ch0 = chunk * p.chunk_c + j * 8;
+  const int g0 = chunk * p.gc;
+  const int r0 = blockIdx.x * p.rows_per_cta, r1 = min(p.hw, r0 + p.rows_per_cta);
+  const long long off = ((long long)b * p.hw) * p.c + ch0;
+  const float inv_n = 1.f / ((float)p.hw * (float)p.cg);
+  // a vector of 8 channels spans at most two groups (cg >= 8): channels [0, nb) belong to group gl0, the rest to gl0 + 1
+  const int gl0 = (j * 8) / p.cg;
+  const int nb = min(8, (gl0 + 1) * p.cg - j * 8);
+  uint4 vxh[R], vdx[R];  // raw x / dy, then packed xhat / dxhat
+  float rs_lo = 0.f, rs_hi = 0.f;
+  {
+    float a1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const int rr = r0 + lane_row + u * p.lanes;
+        if (rr < r1) {
+          vxh[u] = *reinterpret_cast<const uint4*>(p.x + off + (long long)rr * p.c);
+          vdx[u] = *reinterpret_cast<const uint4*>(p.dy + off + (long long)rr * p.c);
+        }
+      }
+      float gam[8], bet[8], sh[8];  // xhat = x * rs + sh,  sh = (xb - mean) * rs
+      load8(p.gamma + ch0, gam);
+      load8(p.beta + ch0, bet);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sh[i] = 0.f;
+      if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.c + ch0), sh);
+      {
+        const float* st = p.stats + ((long long)b * kGnGroups + g0 + gl0) * 2;
+        const float mean_lo = st[0] * inv_n;
+        rs_lo = rsqrtf(fmaxf(st[1] * inv_n - mean_lo * mean_lo, 0.f) + p.eps);
+        float mean_hi = 0.f;
+        if (nb < 8) {
+          mean_hi = st[2] * inv_n;
+          rs_hi = rsqrtf(fmaxf(st[3] * inv_n - mean_hi * mean_hi, 0.f) + p.eps);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sh[i] = (sh[i] - (i < nb ? mean_lo : mean_hi)) * (i < nb ? rs_lo : rs_hi);
+      }
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        if (r0 + lane_row + u * p.lanes < r1) {
+          float f[8], d[8];
+          unpack8(vxh[u], f);
+          unpack8(vdx[u], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = fmaf(f[i], i < nb ? rs_lo : rs_hi, sh[i]);
+            float dz = d[i];
+            if (SILU) dz *= dsilu_f(fmaf(xh, gam[i], bet[i]));
+            const float dxh = dz * gam[i];
+            a1[i] += dxh;
+            a2[i] = fmaf(dxh, xh, a2[i]);
+            f[i] = xh;
+            d[i] = dxh;
+          }
+          vxh[u] = pack8(f);
+          vdx[u] = pack8(d);
+        }
+      }
+    }
+    gn_cta_group_sums(gn_smem, red, a1, a2, active, lane_row, j, p);
+  }
+  gn_cluster_totals(red, tot, 2 * p.gc);
+  if (blockIdx.x == 0 && (int)threadIdx.x < 2 * p.gc && p.bstats)
+    p.bstats[((long long)b * kGnGroups + g0) * 2 + threadIdx.x] = tot[threadIdx.x];
+  if (!active) return;
+  // dx = rs * (dxhat - m1 - xhat * m2) = dxhat * rs - q - xhat * pm,  q = rs * m1,  pm = rs * m2
+  const float q_lo = rs_lo * tot[2 * gl0] * inv_n, pm_lo = rs_lo * tot[2 * gl0 + 1] * inv_n;
+  const float q_hi = nb < 8 ? rs_hi * tot[2 * gl0 + 2] * inv_n : 0.f, pm_hi = nb < 8 ? rs_hi * tot[2 * gl0 + 3] * inv_n : 0.f;
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const int rr = r0 + lane_row + u * p.lanes;
+    if (rr < r1) {
+      float f[8], d[8];
+      unpack8(vxh[u], f);
+      unpack8(vdx[u], d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = fmaf(d[i], i < nb ? rs_lo : rs_hi, -(i < nb ? q_lo : q_hi));
+        f[i] = fmaf(-f[i], i < nb ? pm_lo : pm_hi, t);
+      }
+      *reinterpret_cast<uint4*>(p.out + off + (long long)rr * p.c) = pack8(f);
+    }
+  }
+}
+
+template <typename K>
+static int gn_cluster_launch(K kernel, const GnClusterParams& p, int cs, int n_chunks, int batch, int threads, size_t smem,
+                             cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs, n_chunks, batch);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // co-residency: B200 fits 15 clusters of 8 one-CTA-per-SM blocks (one GPC is short of 16 SMs); a third wave loses
+  int max_clusters = 0;
+  STA_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+  // two waves still beat the two-pass path (18.8 vs 26.9 us for the [2, 4096, 320] gradient: 16 clusters, 15 fit)
+  static const int waves = getenv("STA_GN_MAX_WAVES") ? atoi(getenv("STA_GN_MAX_WAVES")) : 2;
+  if (max_clusters * waves < n_chunks * batch) return -1;  // caller falls back to the two-pass kernels
+  STA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, p));
+  return STA_OK;
+}
+
+// Plans and launches the cluster kernel; *launched = false when the shape does not fit (caller falls back to two passes).
+static int gn_cluster(const sta_groupnorm_args* a, bool bwd, cudaStream_t s, bool* launched) {
+  static const bool off = getenv("STA_GN_TWO_PASS") != nullptr;  // A/B timing and debugging
+  *launched = false;
+  if (off) return STA_OK;
+  const int cg = a->channels / kGnGroups;
+  int gc = 1;
+  while ((gc * cg) % 8 != 0) gc <<= 1;  // whole groups forming whole 16-byte vectors: gc in {1, 2, 4, 8}
+  if (gc > 4 || cg < 8) return STA_OK;  // (the backward's lo / hi split assumes a vector spans <= 2 groups)
+  const int chunk_c = gc * cg, vpr = chunk_c / 8, n_chunks = kGnGroups / gc;
+  const int t_target = bwd ? 640 : 320, r_max = bwd ? 4 : 8;
+  if (vpr > t_target) return STA_OK;
+  const int lanes = t_target / vpr;
+  const int threads = ((lanes * vpr + 31) / 32) * 32;
+  // cluster size: enough CTAs to keep R <= r_max, and (if the rows allow it) >= ~128 CTAs in flight
+  int cs = 1;
+  while (cs < 8 && ((a->hw + cs - 1) / cs + lanes - 1) / lanes > r_max) cs <<= 1;
+  while (cs < 8 && cs * n_chunks * a->batch < 128 && a->hw / (2 * cs) >= lanes) cs <<= 1;
+  const int rows_per_cta = (a->hw + cs - 1) / cs;
+  const int r = (rows_per_cta + lanes - 1) / lanes;
+  if (r > r_max) return STA_OK;
+  GnClusterParams p{};
+  p.x = reinterpret_cast<const __half*>(a->x);
+  p.dy = reinterpret_cast<const __half*>(a->d_out);
+  p.xb = reinterpret_cast<const __half*>(a->x_bias);
+  p.gamma = a->gamma; p.beta = a->beta;
+  p.out = reinterpret_cast<__half*>(a->out);
+  p.stats = a->stats; p.bstats = a->bwd_stats;
+  p.hw = a->hw; p.c = a->channels; p.cg = cg; p.chunk_c = chunk_c; p.gc = gc; p.vpr = vpr; p.lanes = lanes;
+  p.rows_per_cta = rows_per_cta; p.silu = a->silu; p.eps = a->eps;
+  const size_t smem = sizeof(float4) * (size_t)threads;  // one (lo, hi) partial pair per thread
+  int rc;
+  if (!bwd) {
+    if (r <= 1) rc = gn_cluster_launch(gn_cluster_fwd_kernel<1>, p, cs, n_chunks, a->batch, threads, smem, s);
+    else if (r <= 2) rc = gn_cluster_launch(gn_cluster_fwd_kernel<2>, p, cs, n_chunks, a->batch, threads, smem, s);
+    else if (r <= 4) rc = gn_cluster_launch(gn_cluster_fwd_kernel<4>, p, cs, n_chunks, a->batch, threads, smem, s);
+    else rc = gn_cluster_launch(gn_cluster_fwd_kernel<8>, p, cs, n_chunks, a->batch, threads, smem, s);
+  } else if (a->silu) {
+    if (r <= 1) rc = gn_cluster_launch(gn_cluster_bwd_kernel<1, true>, p, cs, n_chunks, a->batch, threads, smem, s);
+    else if (r <= 2) rc = gn_cluster_launch(gn_cluster_bwd_kernel<2, true>, p, cs, n_chunks, a->batch, threads, smem, s);
+    else rc = gn_cluster_launch(gn_cluster_bwd_kernel<4, true>, p, cs, n_chunks, a->batch, threads, smem, s);
+  } else {
+    if (r <= 1) rc = gn_cluster_launch(gn_cluster_bwd_kernel<1, false>, p, cs, n_chunks, a->batch, threads, smem, s);
+    else if (r <= 2) rc = gn_cluster_launch(gn_cluster_bwd_kernel<2, false>, p, cs, n_chunks, a->batch, threads, smem, s);
+    else rc = gn_cluster_launch(gn_cluster_bwd_kernel<4, false>, p, cs, n_chunks, a->batch, threads, smem, s);
+  }
+  if (rc == -1) return STA_OK;  // does not fit one wave
+  if (rc) return rc;
+  *launched = true;
+  return STA_OK;
+}
+
 }  // namespace sta
 
 extern "C" int sta_groupnorm_fwd(const sta_groupnorm_args* a, void* stream) {
@@ -354,9 +684,14 @@ extern "C" int sta_groupnorm_fwd(const sta_groupnorm_args* a, void* stream) {
   p.gamma = a->gamma; p.beta = a->beta; p.stats = a->stats;
   p.batch = a->batch; p.hw = a->hw; p.c = a->channels; p.rows_per_block = L.rows_per_block; p.silu = a->silu;
   p.lanes = L.lanes; p.eps = a->eps;
-  STA_CUDA_CHECK(cudaMemsetAsync(a->stats, 0, sizeof(float) * a->batch * kGnGroups * 2, s));
-  gn_stats_kernel<<<L.grid, L.threads, L.smem, s>>>(p);
-  gn_apply_kernel<<<L.grid, L.threads, 0, s>>>(p);
+  bool launched = false;
+  rc = gn_cluster(a, false, s, &launched);
+  if (rc) return rc;
+  if (!launched) {
+    STA_CUDA_CHECK(cudaMemsetAsync(a->stats, 0, sizeof(float) * a->batch * kGnGroups * 2, s));
+    gn_stats_kernel<<<L.grid, L.threads, L.smem, s>>>(p);
+    gn_apply_kernel<<<L.grid, L.threads, 0, s>>>(p);
+  }
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }
@@ -377,9 +712,19 @@ extern "C" int sta_groupnorm_bwd(const sta_groupnorm_args* a, void* stream) {
   p.gamma = a->gamma; p.beta = a->beta; p.stats = a->stats; p.bstats = a->bwd_stats;
   p.batch = a->batch; p.hw = a->hw; p.c = a->channels; p.rows_per_block = L.rows_per_block; p.silu = a->silu;
   p.lanes = L.lanes; p.eps = a->eps;
-  STA_CUDA_CHECK(cudaMemsetAsync(a->bwd_stats, 0, sizeof(float) * a->batch * kGnGroups * 2, s));
-  gn_bwd_stats_kernel<<<L.grid, L.threads, L.smem, s>>>(p);
-  gn_bwd_apply_kernel<<<L.grid, L.threads, 0, s>>>(p);
+  bool launched = false;
+  rc = gn_cluster(a, true, s, &launched);
+  if (rc) return rc;
+  if (!launched) {
+    STA_CUDA_CHECK(cudaMemsetAsync(a->bwd_stats, 0, sizeof(float) * a->batch * kGnGroups * 2, s));
+    if (a->silu) {
+      gn_bwd_stats_kernel<true><<<L.grid, L.threads, L.smem, s>>>(p);
+      gn_bwd_apply_kernel<true><<<L.grid, L.threads, 0, s>>>(p);
+    } else {
+      gn_bwd_stats_kernel<false><<<L.grid, L.threads, L.smem, s>>>(p);
+      gn_bwd_apply_kernel<false><<<L.grid, L.threads, 0, s>>>(p);
+    }
+  }
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }

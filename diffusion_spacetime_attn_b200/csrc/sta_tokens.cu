@@ -62,29 +62,51 @@ struct LnParams {
   const __half* dsum;
   __half* dx;
   int rows, c;
+  int tpr;  // threads per row: 8, 16 or 32 (a warp holds 32 / tpr rows)
   float eps;
 };
 
 constexpr int kLnWarps = 4;
 
-// one warp per row; lane owns vectors lane, lane+32, ... (NV of them, the tail predicated off)
+// sum over the tpr consecutive lanes that share a row
+__device__ __forceinline__ float row_sum(float v, int tpr) {
+  for (int o = tpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// tpr lanes per row (32 / tpr rows per warp); a lane owns vectors sub, sub + tpr, ... (NV of them, the tail predicated
+// off).  SD-v1 widths are 40 * 2^k vectors -> tpr = 8 * 2^k, NV = 5: no idle lanes, 5 independent 16-byte loads in flight.
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
-  const int lane = threadIdx.x & 31, row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  const int tpr = p.tpr, rpw = 32 / tpr;
+  const int lane = threadIdx.x & (tpr - 1);
+  int row = (blockIdx.x * kLnWarps + (threadIdx.x >> 5)) * rpw + ((threadIdx.x & 31) / tpr);
+  const bool live = row < p.rows;  // dead rows still take part in the shuffles
+  if (!live) row = p.rows - 1;
   const int vecs = p.c >> 3;
   const long long base = (long long)row * p.c;
+  // phase 1: every load of the row is issued before the first store (sum_out may alias nothing, but the compiler cannot
+  // know: a store between two loads would serialise NV global round trips)
+  uint4 xv[NV], rv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + tpr * i;
+    if (vi < vecs) {
+      xv[i] = *reinterpret_cast<const uint4*>(p.x + base + vi * 8);
+      if (p.res) rv[i] = *reinterpret_cast<const uint4*>(p.res + base + vi * 8);
+    }
+  }
   float v[NV][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + 32 * i;
+    const int vi = lane + tpr * i;
     if (vi < vecs) {
-      tk_unpack8(*reinterpret_cast<const uint4*>(p.x + base + vi * 8), v[i]);
+      tk_unpack8(xv[i], v[i]);
       bool rounded = true;
       if (p.res) {
         float r[8];
-        tk_unpack8(*reinterpret_cast<const uint4*>(p.res + base + vi * 8), r);
+        tk_unpack8(rv[i], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] += r[j];
         rounded = false;
@@ -97,9 +119,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
         rounded = false;
       }
       if (!rounded) {  // the sum is stored in fp16; normalise exactly what the backward will read back
-        const uint4 o = tk_pack8(v[i]);
-        if (p.sum_out) *reinterpret_cast<uint4*>(p.sum_out + base + vi * 8) = o;
-        tk_unpack8(o, v[i]);
+        xv[i] = tk_pack8(v[i]);
+        tk_unpack8(xv[i], v[i]);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
@@ -108,13 +129,20 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
       for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
     }
   }
+  if (p.sum_out && live && (p.res || p.bias)) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + tpr * i;
+      if (vi < vecs) *reinterpret_cast<uint4*>(p.sum_out + base + vi * 8) = xv[i];
+    }
+  }
   if (!p.gamma) return;
   const float inv_c = 1.f / (float)p.c;
-  const float mean = warp_sum(s) * inv_c;
+  const float mean = row_sum(s, tpr) * inv_c;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    if (lane + 32 * i < vecs) {
+    if (lane + tpr * i < vecs) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = v[i][j] - mean;
@@ -122,12 +150,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) * inv_c + p.eps);
-  if (p.stats && lane == 0) *reinterpret_cast<float2*>(p.stats + 2 * (long long)row) = make_float2(mean, rstd);
+  const float rstd = rsqrtf(row_sum(q, tpr) * inv_c + p.eps);
+  if (p.stats && lane == 0 && live) *reinterpret_cast<float2*>(p.stats + 2 * (long long)row) = make_float2(mean, rstd);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < vecs) {
+    const int vi = lane + tpr * i;
+    if (vi < vecs && live) {
       float g[8], b[8], o[8];
       load8f(p.gamma + vi * 8, g);
       load8f(p.beta + vi * 8, b);
@@ -141,8 +169,11 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
 // dx = dsum + rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat))
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(LnParams p) {
-  const int lane = threadIdx.x & 31, row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
-  if (row >= p.rows) return;
+  const int tpr = p.tpr, rpw = 32 / tpr;
+  const int lane = threadIdx.x & (tpr - 1);
+  int row = (blockIdx.x * kLnWarps + (threadIdx.x >> 5)) * rpw + ((threadIdx.x & 31) / tpr);
+  const bool live = row < p.rows;
+  if (!live) row = p.rows - 1;
   const int vecs = p.c >> 3;
   const long long base = (long long)row * p.c;
   const float2 st = *reinterpret_cast<const float2*>(p.stats + 2 * (long long)row);
@@ -151,7 +182,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(LnParams p) {
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + 32 * i;
+    const int vi = lane + tpr * i;
     if (vi < vecs) {
       float gam[8];
       tk_unpack8(*reinterpret_cast<const uint4*>(p.dy + base + vi * 8), g[i]);
@@ -167,12 +198,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(LnParams p) {
     }
   }
   const float inv_c = 1.f / (float)p.c;
-  s1 = warp_sum(s1) * inv_c;
-  s2 = warp_sum(s2) * inv_c;
+  s1 = row_sum(s1, tpr) * inv_c;
+  s2 = row_sum(s2, tpr) * inv_c;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < vecs) {
+    const int vi = lane + tpr * i;
+    if (vi < vecs && live) {
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
@@ -205,6 +236,20 @@ static int ln_shape_ok(int rows, int channels, const char* who) {
   if (channels % 8 != 0 || channels > 2048)
     return fail(STA_ERR_UNSUPPORTED, "%s: channels %d must be a multiple of 8 and <= 2048", who, channels);
   return STA_OK;
+}
+
+// threads per row in {8, 16, 32}: the smallest that keeps <= 8 vectors per thread, preferring the one that wastes
+// the fewest lanes (vecs = 40 -> 8 x 5, 80 -> 16 x 5, 160 -> 32 x 5)
+static int ln_threads_per_row(int vecs, int* nv_out) {
+  int best = 32, best_nv = (vecs + 31) / 32, best_waste = best_nv * 32 - vecs;
+  for (int tpr = 16; tpr >= 8; tpr >>= 1) {
+    const int nv = (vecs + tpr - 1) / tpr;
+    if (nv > 8) break;
+    const int waste = nv * tpr - vecs;
+    if (waste <= best_waste) { best = tpr; best_nv = nv; best_waste = waste; }
+  }
+  *nv_out = best_nv;
+  return best;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -284,8 +329,10 @@ extern "C" int sta_add_layernorm_fwd(const sta_add_layernorm_args* a, void* stre
   p.y = reinterpret_cast<__half*>(a->y);
   p.stats = a->stats;
   p.rows = a->rows; p.c = a->channels; p.eps = a->eps;
-  const int nv = (a->channels / 8 + 31) / 32;
-  const unsigned grid = (unsigned)((a->rows + kLnWarps - 1) / kLnWarps);
+  int nv;
+  p.tpr = ln_threads_per_row(a->channels / 8, &nv);
+  const int rows_per_block = kLnWarps * (32 / p.tpr);
+  const unsigned grid = (unsigned)((a->rows + rows_per_block - 1) / rows_per_block);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   STA_LN_DISPATCH(add_ln_fwd_kernel, nv, grid, s, p);
   STA_CUDA_CHECK(cudaGetLastError());
@@ -309,8 +356,10 @@ extern "C" int sta_add_layernorm_bwd(const sta_add_layernorm_bwd_args* a, void* 
   p.gamma = a->gamma;
   p.dx = reinterpret_cast<__half*>(a->d_x);
   p.rows = a->rows; p.c = a->channels;
-  const int nv = (a->channels / 8 + 31) / 32;
-  const unsigned grid = (unsigned)((a->rows + kLnWarps - 1) / kLnWarps);
+  int nv;
+  p.tpr = ln_threads_per_row(a->channels / 8, &nv);
+  const int rows_per_block = kLnWarps * (32 / p.tpr);
+  const unsigned grid = (unsigned)((a->rows + rows_per_block - 1) / rows_per_block);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   STA_LN_DISPATCH(add_ln_bwd_kernel, nv, grid, s, p);
   STA_CUDA_CHECK(cudaGetLastError());

@@ -5,14 +5,39 @@ Reference: ldm/models/autoencoder.py:285-333 (AutoencoderKL.decode) -> ldm/modul
 epoch, differentiably: ddpm.py:705 has @no_grad commented out); the encoder is not built (checkpoint keys for it are
 ignored by load_state_dict(strict=False), as the reference does at scripts/txt2img-gpt.py:62).
 
-Out of the kernel scope: this stays PyTorch/cuDNN.  The single mid-block attention
-(1 head, d = 512, N = 4096) goes through torch's fused SDPA instead of materialising the 4096^2 matrix.
+SURVEY.md §8f rank 3.  The convolutions stay cuDNN; on fp16 CUDA activations (what the pipeline feeds it) everything
+between them runs on this package's streaming kernels, NHWC end to end:
+  * GroupNorm(32) + SiLU -> sta_groupnorm (one fused pass pair instead of fp32 copy / moments / normalise / fp16 copy /
+    SiLU on NCHW tensors — the reference's chain was 65 % of the decode + loss + backward time on B200);
+  * conv1's bias rides in the second GroupNorm (x_bias), conv2's bias (+ the 1x1 shortcut's) and the residual add are
+    one pass (sta_add_layernorm_fwd without a norm) — ATen adds a cuDNN conv bias as a separate broadcast kernel;
+  * the 1x1 convolutions (shortcut, attention q/k/v/proj_out) are token GEMMs on the NHWC memory; q/k/v are ONE GEMM.
+The single mid-block attention (1 head, d = 512, N = 4096) is bmm / softmax / bmm as in the reference (model.py:176-191) on
+the fused path, torch SDPA on the plain path.  On CPU / fp32 tensors the plain torch path below runs
+(that is what tests/test_vae_golden.py checks against the reference's output on CPU).
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from ... import ops
+from ..modules.attention import _frozen, cached_sum, nhwc_tokens, tokens_nhwc
+
+
+def _fusable(x: torch.Tensor, module: nn.Module) -> bool:
+    return x.is_cuda and x.dtype == torch.float16 and _frozen(module)
+
+
+def _gn(owner: nn.Module, tag: str, norm: nn.GroupNorm, x, silu: bool, x_bias=None):
+    f32 = torch.float32
+    return ops.group_norm_silu(x, cached_sum(owner, tag + "w", [norm.weight], f32), cached_sum(owner, tag + "b", [norm.bias], f32),
+                               norm.eps, silu, x_bias=x_bias)
+
+
+def _conv_nobias(owner: nn.Module, tag: str, conv: nn.Conv2d, x):
+    return F.conv2d(x, cached_sum(owner, tag, [conv.weight], torch.float16), None, conv.stride, conv.padding)
 
 
 def Normalize(in_channels, num_groups=32):
@@ -44,7 +69,27 @@ class ResnetBlock(nn.Module):
         if in_channels != out_channels:
             self.nin_shortcut = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, padding=0)
 
+    def _forward_fused(self, x):
+        b, c, hh, ww = x.shape
+        f16 = torch.float16
+        with torch.autocast("cuda", enabled=False):
+            h = _conv_nobias(self, "w1", self.conv1, _gn(self, "n1", self.norm1, x, True))
+            xb = cached_sum(self, "b1", [self.conv1.bias], f16)
+            xb = xb.unsqueeze(0) if b == 1 else xb.unsqueeze(0).expand(b, -1).contiguous()
+            h = _conv_nobias(self, "w2", self.conv2, _gn(self, "n2", self.norm2, h, True, x_bias=xb))
+            x_tok = nhwc_tokens(x)
+            if self.in_channels != self.out_channels:
+                sk = self.nin_shortcut
+                skip = F.linear(x_tok, cached_sum(self, "ws", [sk.weight], f16).reshape(self.out_channels, c))
+                bias = cached_sum(self, "bo", [self.conv2.bias, sk.bias], torch.float32)
+            else:
+                skip = x_tok if x_tok.is_contiguous() else x_tok.contiguous()
+                bias = cached_sum(self, "bo", [self.conv2.bias], torch.float32)
+            return tokens_nhwc(ops.bias_residual_add(nhwc_tokens(h), bias, skip), hh, ww)
+
     def forward(self, x, temb=None):
+        if _fusable(x, self) and (not self.training or self.dropout.p == 0.0):
+            return self._forward_fused(x)
         h = self.conv1(F.silu(self.norm1(x)))
         h = self.conv2(self.dropout(F.silu(self.norm2(h))))
         if self.in_channels != self.out_channels:
@@ -61,7 +106,35 @@ class AttnBlock(nn.Module):
         self.v = nn.Conv2d(in_channels, in_channels, kernel_size=1)
         self.proj_out = nn.Conv2d(in_channels, in_channels, kernel_size=1)
 
+    def _forward_fused(self, x):
+        b, c, hh, ww = x.shape
+        f16 = torch.float16
+        with torch.autocast("cuda", enabled=False):
+            t = nhwc_tokens(_gn(self, "n", self.norm, x, False))  # [b, hw, c]
+            slot = self.__dict__.setdefault("_sta_cached", {})
+            key = tuple((m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version) for m in (self.q, self.k, self.v))
+            if slot.get("qkv", (None,))[0] != key:
+                with torch.no_grad():
+                    wq = torch.cat([m.weight.detach().reshape(c, c) for m in (self.q, self.k, self.v)]).to(f16).contiguous()
+                    bq = torch.cat([m.bias.detach() for m in (self.q, self.k, self.v)]).to(f16).contiguous()
+                slot["qkv"] = (key, wq, bq)
+            _, wq, bq = slot["qkv"]
+            q, k, v = F.linear(t, wq, bq).chunk(3, dim=-1)  # [b, hw, c] views
+            # One head of d = 512: torch's SDPA falls back to an sm80 memory-efficient kernel here (3.1 ms backward on
+            # B200, 28 TFLOP/s).  The 4096^2 score matrix is 32 MB in fp16 — the reference materialises it as well
+            # (model.py:176-191) — so this is bmm / softmax / bmm on cuBLAS, fp32 softmax as under autocast.
+            w_ = torch.bmm(q, k.transpose(1, 2))
+            w_ = torch.softmax(w_.float() * (int(c) ** -0.5), dim=2).to(f16)
+            o = torch.bmm(w_, v)
+            o = F.linear(o, cached_sum(self, "wo", [self.proj_out.weight], f16).reshape(c, c))
+            x_tok = nhwc_tokens(x)
+            x_tok = x_tok if x_tok.is_contiguous() else x_tok.contiguous()
+            out = ops.bias_residual_add(o, cached_sum(self, "bo", [self.proj_out.bias], torch.float32), x_tok)
+            return tokens_nhwc(out, hh, ww)
+
     def forward(self, x):
+        if _fusable(x, self):
+            return self._forward_fused(x)
         h_ = self.norm(x)
         b, c, h, w = h_.shape
         q, k, v = (f(h_).reshape(b, 1, c, h * w).transpose(2, 3) for f in (self.q, self.k, self.v))
@@ -106,6 +179,8 @@ class Decoder(nn.Module):
                 h = self.up[i_level].block[i_block](h)
             if i_level != 0:
                 h = self.up[i_level].upsample(h)
+        if _fusable(h, self.norm_out):
+            return self.conv_out(_gn(self, "no", self.norm_out, h, True))
         return self.conv_out(F.silu(self.norm_out(h)))
 
 
@@ -119,4 +194,4 @@ class AutoencoderKL(nn.Module):
         self.embed_dim = embed_dim
 
     def decode(self, z):
-        return self.decoder(self.post_quant_conv(z))
+        return self.decoder(self.post_quant_conv(z.to(self.post_quant_conv.weight.dtype)))

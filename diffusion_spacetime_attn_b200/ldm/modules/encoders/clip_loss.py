@@ -101,6 +101,21 @@ class CLIPViTB32(nn.Module):
         return self.load_state_dict({k: v for k, v in sd.items() if k in self.state_dict()}, strict=False)
 
 
+def upsample_avgpool_matrix(size_in: int, scale: int = 7, pool: int = 16) -> torch.Tensor:
+    """The reference's global-loss resampling, nn.Upsample(scale_factor=7) (nearest) followed by nn.AvgPool2d(16)
+    (plms.py:26-27,41), is a fixed separable linear map: out = A @ img @ A^T with A [size_in*scale/pool, size_in],
+    A[i, r // scale] += 1/pool for r in [pool*i, pool*(i+1)).  Two tiny GEMMs instead of materialising the 3584 x 3584
+    fp32 image and pooling it back (and the same again in backward) — SURVEY.md §8f rank 4."""
+    up = size_in * scale
+    if up % pool:
+        raise ValueError(f"{size_in} x {scale} is not a multiple of the {pool}-pixel pooling window")
+    A = torch.zeros(up // pool, size_in, dtype=torch.float64)
+    src = torch.arange(up) // scale
+    rows = torch.arange(up) // pool
+    A.index_put_((rows, src), torch.full((up,), 1.0 / pool, dtype=torch.float64), accumulate=True)
+    return A.float()
+
+
 def hash_tokenize(texts: List[str], context_length: int = 77, vocab_size: int = 49408) -> torch.Tensor:
     """Offline stand-in for clip.tokenize (its BPE vocabulary is not in this image): <sot> word-hash ids <eot>."""
     out = torch.zeros(len(texts), context_length, dtype=torch.long)
@@ -123,6 +138,7 @@ class DCLIPLoss(nn.Module):
         self.avg_pool = nn.AvgPool2d(kernel_size=16)
         self.tokenizer = tokenizer or hash_tokenize
         self._text_cache = {}
+        self._resample = {}
 
     def _text_feat(self, text):
         if text not in self._text_cache:
@@ -137,7 +153,18 @@ class DCLIPLoss(nn.Module):
 
     def forward_2(self, image, text):
         """Global loss: image [3, 512, 512] in [0,1] -> 1 - cos(CLIP(img), CLIP(text))   (plms.py:38-45)."""
-        return self._one_minus_cos(self.avg_pool(self.upsample(image.unsqueeze(0))), text)
+        h, w = image.shape[-2:]
+        if (h * 7) % 16 or (w * 7) % 16:  # AvgPool2d floors odd sizes: keep the literal ops for those
+            return self._one_minus_cos(self.avg_pool(self.upsample(image.unsqueeze(0))), text)
+        mats = []
+        for n in (h, w):
+            key = (n, image.device)
+            if key not in self._resample:
+                self._resample[key] = upsample_avgpool_matrix(n).to(image.device)
+            mats.append(self._resample[key])
+        with torch.autocast(image.device.type, enabled=False):  # exact fp32, like the reference's pooling of an fp32 image
+            small = mats[0] @ image.float() @ mats[1].t()
+        return self._one_minus_cos(small.unsqueeze(0), text)
 
     def forward_3(self, image, text):
         """Per-object crop loss with a bilinear resize to 224 x 224   (plms.py:29-36)."""

@@ -145,6 +145,13 @@ class SpaceTimeAttnPipeline:
             # NHWC activations/weights: cuDNN's fp16 tensor-core convolutions are NHWC natively (removes the
             # nchwToNhwc transposes, ~20 % of an evaluation) and 'b c h w -> b (h w) c' becomes a free view
             unet.to(memory_format=torch.channels_last)
+            vae = self.model.first_stage_model
+            if vae is not None:  # same treatment for the KL-VAE decoder (fused NHWC GroupNorm / bias / residual kernels)
+                vae.half()
+                for m in vae.modules():
+                    if isinstance(m, torch.nn.GroupNorm):
+                        m.float()
+                vae.to(memory_format=torch.channels_last)
         self.cuda_graphs = cuda_graphs
         if cuda_graphs:
             from .graphed import GraphedModelRunner
@@ -156,6 +163,14 @@ class SpaceTimeAttnPipeline:
         self.text = SyntheticTextEmbedder(device="cpu")
         self.model.cond_stage_model = self.text
         self.clip_loss = DCLIPLoss(device=self.device, seed=seed + 1) if with_vae else torch.nn.Identity()
+        if half_weights and with_vae:
+            # fp16 CLIP weights (fp32 LayerNorms): what autocast computes from fp32 masters, minus ~460 cast launches
+            # per loss evaluation.  The text features are cached per prompt in fp32.
+            clip = self.clip_loss.model
+            clip.half()
+            for m in clip.modules():
+                if isinstance(m, torch.nn.LayerNorm):
+                    m.float()
         cls = DDIMSampler if sampler == "ddim" else PLMSSampler
         self.sampler = cls(self.model, clip_loss_model=self.clip_loss, num_epochs=num_epochs, save_images=save_images,
                            out_dir=out_dir)

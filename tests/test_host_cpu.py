@@ -118,3 +118,24 @@ def test_object_crop_box_matches_reference_expression():
     assert O.object_crop_box([0.3, 0.5]) == (int(512 * 0.3), int(512 * 0.7), int(512 * (0.3 - 0.2)), int(512 * 0.5))
     assert O.object_crop_box([0.05, 0.95]) == (int(512 * 0.75), 512, 0, int(512 * 0.25))
     assert float(O.alpha_init(2, 50)[0, 0]) == 2.5 and tuple(O.alpha_init(3, 10).shape) == (3, 10)
+
+
+def test_clip_global_resample_matrix_equals_upsample_avgpool():
+    """plms.py:26-27,41: Upsample(x7, nearest) -> AvgPool2d(16) == A @ img @ A^T, incl. gradients."""
+    import torch.nn as nn
+
+    from diffusion_spacetime_attn_b200.ldm.modules.encoders.clip_loss import upsample_avgpool_matrix
+
+    g = torch.Generator().manual_seed(3)
+    for h, w in ((512, 512), (64, 96), (16, 16)):
+        img = torch.rand(3, h, w, generator=g, requires_grad=True)
+        ref = nn.AvgPool2d(16)(nn.Upsample(scale_factor=7)(img.unsqueeze(0)))[0]
+        G = torch.randn(ref.shape, generator=g)
+        (gref,) = torch.autograd.grad((ref * G).sum(), img)
+        A, B = upsample_avgpool_matrix(h), upsample_avgpool_matrix(w)
+        out = A @ img @ B.t()
+        (gout,) = torch.autograd.grad((out * G).sum(), img)
+        assert out.shape == ref.shape == (3, h * 7 // 16, w * 7 // 16)
+        assert (out - ref).abs().max().item() < 1e-5
+        assert (gout - gref).abs().max().item() < 1e-5
+        assert torch.allclose(A.sum(1), torch.ones(A.shape[0]))

@@ -31,7 +31,10 @@ def short(name: str) -> str:
     return name[:150]
 
 
-for label, graph in (("forward graph", g.g_fwd), ("recompute+backward graph", g.g_bwd)):
+graphs = [("forward graph (no grad)", g.g_fwd), ("recompute+backward graph", g.g_bwd)]
+if g.slots:  # what a differentiable evaluation actually replays: forward-with-grad + backward-only of one slot
+    graphs = [("slot forward graph (activations kept)", g.slots[0].g_fwd), ("slot backward graph", g.slots[0].g_bwd)]
+for label, graph in graphs:
     for _ in range(2):
         graph.replay()
     torch.cuda.synchronize()
