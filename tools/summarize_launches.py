@@ -11,8 +11,14 @@ rd = csv.DictReader(lines)
 for r in rd:
     if r.get("Metric Name") != "gpu__time_duration.sum":
         continue
-    name = re.sub(r"\(.*", "", r["Kernel Name"])
-    name = re.sub(r"<.*", "", name)
+    name = r["Kernel Name"]
+    if "sta::" in name:
+        name = re.sub(r"\(.*", "", name)  # keep the template arguments of our own kernels (head dim, rows per thread)
+    else:
+        name = re.sub(r"\[lambda[^\]]*\]", "L", re.sub(r"std::array<[^>]*>", "arr", name))
+        m = re.match(r"(void )?(at::native::)?(\(anonymous namespace\)::)?([A-Za-z0-9_:]+)(<[^(]{0,120})?", name)
+        name = (m.group(4) + (m.group(5) or "")) if m else name[:120]
+    name = name.replace(",", ";")[:140]
     v = float(r["Metric Value"].replace(",", ""))
     unit = r["Metric Unit"]
     v_us = v / 1000.0 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1000.0)
