@@ -154,13 +154,17 @@ class DCLIPLoss(nn.Module):
     def forward_2(self, image, text):
         """Global loss: image [3, 512, 512] in [0,1] -> 1 - cos(CLIP(img), CLIP(text))   (plms.py:38-45)."""
         h, w = image.shape[-2:]
-        if (h * 7) % 16 or (w * 7) % 16:  # AvgPool2d floors odd sizes: keep the literal ops for those
-            return self._one_minus_cos(self.avg_pool(self.upsample(image.unsqueeze(0))), text)
+        # 512 px: Upsample(x7) -> AvgPool2d(16) -> 224 px, the reference's literal pipeline.  Other sizes (the reference
+        # hard-codes 512, SURVEY.md §8a-note) keep the x7 upsample and pool with the window that lands on CLIP's 224 px
+        # (768 px -> window 24); sizes where that is not an integer are resized bilinearly instead.
+        if (h * 7) % 224 or (w * 7) % 224:
+            img = F.interpolate(image.unsqueeze(0).float(), size=(224, 224), mode="bilinear", antialias=True, align_corners=False)
+            return self._one_minus_cos(img, text)
         mats = []
         for n in (h, w):
             key = (n, image.device)
             if key not in self._resample:
-                self._resample[key] = upsample_avgpool_matrix(n).to(image.device)
+                self._resample[key] = upsample_avgpool_matrix(n, 7, n * 7 // 224).to(image.device)
             mats.append(self._resample[key])
         with torch.autocast(image.device.type, enabled=False):  # exact fp32, like the reference's pooling of an fp32 image
             small = mats[0] @ image.float() @ mats[1].t()

@@ -139,3 +139,21 @@ def test_clip_global_resample_matrix_equals_upsample_avgpool():
         assert (out - ref).abs().max().item() < 1e-5
         assert (gout - gref).abs().max().item() < 1e-5
         assert torch.allclose(A.sum(1), torch.ones(A.shape[0]))
+
+
+def test_clip_global_loss_accepts_non_512_images():
+    """configs[4] decodes 768 px images (the reference hard-codes 512): the x7 upsample is kept and the
+    pooling window becomes 7 * size / 224 so that CLIP still sees 224 x 224; the 512 px case is the reference's literal one."""
+    import torch.nn as nn
+
+    from diffusion_spacetime_attn_b200.ldm.modules.encoders.clip_loss import DCLIPLoss, upsample_avgpool_matrix
+
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(3, 768, 768, generator=g)
+    A = upsample_avgpool_matrix(768, 7, 24)
+    ref = nn.AvgPool2d(24)(nn.Upsample(scale_factor=7)(img.unsqueeze(0)))[0]
+    assert ref.shape == (3, 224, 224) and (A @ img @ A.t() - ref).abs().max().item() < 1e-5
+    loss = DCLIPLoss(device="cpu")
+    for size in (512, 768, 100):  # 100: no integer window -> bilinear resize
+        out = loss.forward_2(torch.rand(3, size, size, generator=g), "a red cube")
+        assert out.shape == (1,) and bool(torch.isfinite(out).all())
