@@ -175,7 +175,12 @@ class GraphedUNetEval:
             if not s.busy:
                 s.busy = True
                 return s
-        s = self._capture_slot()
+        try:
+            s = self._capture_slot()
+        except torch.OutOfMemoryError:  # the budget estimate was too optimistic: keep what exists, recompute the rest
+            self.max_slots = len(self.slots)
+            torch.cuda.empty_cache()
+            s = None
         if s is not None:
             s.busy = True
         return s
