@@ -367,7 +367,7 @@ def run_native(args):
     peaks = measured_peaks()
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"
-    roofline = None
+    roofline = roofline_xattn = None
     if kernels:
         top = kernels[0]
         if tf.exists():
@@ -379,6 +379,16 @@ def run_native(args):
                     "traffic": traffic, "peak_source": peaks["source"], "launches": top["launches"],
                     "mean_launch_us": top["mean_us"], "share_of_step": top["total_ms"] / dev_ms,
                     "flops_convention": "algorithmic, no recompute (SURVEY.md 8d); sattn_bwd = 2.0 x fwd"}
+        # the fused dual cross-attention (north_star's named kernel) is HBM/latency-bound (38.5*(2+n) FLOP/B): reported
+        # against the measured copy bandwidth, with its tensor throughput next to it
+        xa = [k for k in kernels if k["kernel"] == "sta_xattn_fwd"]
+        if xa:
+            x0 = xa[0]
+            tr = json.loads(tf.read_text()).get("sta_xattn_fwd:" + "x".join(map(str, x0["geometry"]))) if tf.exists() else None
+            roofline_xattn = {"kernel": x0["kernel"], "geometry": x0["geometry"], "bound": "hbm", "achieved": x0["gbs"],
+                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": x0["gbs"] / peaks["hbm_gbs"], "traffic": tr,
+                              "mean_launch_us": x0["mean_us"], "tflops": x0["tflops"],
+                              "note": "algorithmic bytes: q + out + projected contexts + masks (SURVEY.md 8d)"}
 
     if rank == 0:
         n_img = args.steps * world
@@ -400,7 +410,8 @@ def run_native(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
-            "kernels": kernels[:8],
+            "roofline_xattn": roofline_xattn,
+            "kernels": kernels[:12],
             "peak_mem_gib": peak_mem,
             "reserved_mem_gib": reserved_mem,
             "device_error": err,
