@@ -26,6 +26,8 @@ EXPORTED_SYMBOLS = (
     "sta_add_layernorm_bwd",
     "sta_geglu_fwd",
     "sta_geglu_bwd",
+    "sta_upsample2x_fwd",
+    "sta_upsample2x_bwd",
     "sta_probe_gemm",
     "sta_probe_tmem_bw",
     "sta_debug_read",
@@ -111,6 +113,11 @@ class GegluArgs(C.Structure):
     _fields_ = [("proj", C.c_void_p), ("d_out", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int32), ("inner", C.c_int32)]
 
 
+class Upsample2xArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+                ("channels", C.c_int32)]
+
+
 class ProbeArgs(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("a_rows", C.c_int32), ("a_tensor_rows", C.c_int32), ("a_cols", C.c_int32),
@@ -147,6 +154,7 @@ def load() -> C.CDLL:
         ("sta_probe_gemm", ProbeArgs), ("sta_groupnorm_fwd", GroupNormArgs), ("sta_groupnorm_bwd", GroupNormArgs),
         ("sta_add_layernorm_fwd", AddLayerNormArgs), ("sta_add_layernorm_bwd", AddLayerNormBwdArgs),
         ("sta_geglu_fwd", GegluArgs), ("sta_geglu_bwd", GegluArgs),
+        ("sta_upsample2x_fwd", Upsample2xArgs), ("sta_upsample2x_bwd", Upsample2xArgs),
     ):
         if not hasattr(lib, name):  # reported by tests/test_cabi.py; calling it raises AttributeError
             continue

@@ -14,7 +14,8 @@ from . import native
 
 # number of kernels launched by this module since import (bench.py reports it as `gpu_launches`)
 LAUNCHES = {"sattn_fwd": 0, "sattn_bwd": 0, "xattn_fwd": 0, "xattn_bwd": 0, "groupnorm_fwd": 0, "groupnorm_bwd": 0,
-            "add_layernorm_fwd": 0, "add_layernorm_bwd": 0, "geglu_fwd": 0, "geglu_bwd": 0, "bias_add": 0}
+            "add_layernorm_fwd": 0, "add_layernorm_bwd": 0, "geglu_fwd": 0, "geglu_bwd": 0, "bias_add": 0,
+            "upsample2x_fwd": 0, "upsample2x_bwd": 0}
 
 
 def launch_count() -> int:
@@ -565,3 +566,43 @@ class GegluFn(torch.autograd.Function):
 def geglu(proj):
     """value * gelu(gate) of a [.., 2*inner] projection (value | gate), fp16 CUDA."""
     return GegluFn.apply(proj)
+
+
+# ------------------------------------------------------------------------------------------------------
+# nearest x2 upsampling, NHWC fp16
+# ------------------------------------------------------------------------------------------------------
+def _upsample2x(x: torch.Tensor, backward: bool) -> torch.Tensor:
+    _require(x, "x")
+    b, c, h, w = x.shape
+    x = _nhwc(x)
+    if backward:
+        if h % 2 or w % 2:
+            raise RuntimeError("upsample2x backward needs even spatial sizes")
+        lo_h, lo_w = h // 2, w // 2
+        out = torch.empty((b, c, lo_h, lo_w), device=x.device, dtype=torch.float16, memory_format=torch.channels_last)
+    else:
+        lo_h, lo_w = h, w
+        out = torch.empty((b, c, 2 * h, 2 * w), device=x.device, dtype=torch.float16, memory_format=torch.channels_last)
+    a = native.Upsample2xArgs()
+    a.x, a.out, a.batch, a.height, a.width, a.channels = x.data_ptr(), out.data_ptr(), b, lo_h, lo_w, c
+    kind = "upsample2x_bwd" if backward else "upsample2x_fwd"
+    with _timed(kind, (b, lo_h * lo_w, c)):
+        fn = native.load().sta_upsample2x_bwd if backward else native.load().sta_upsample2x_fwd
+        native.check(fn(C.byref(a), _stream()), "sta_" + kind)
+    LAUNCHES[kind] += 1
+    return out
+
+
+class Upsample2xFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _upsample2x(x, False)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        return _upsample2x(d_out if d_out.dtype == torch.float16 else d_out.to(torch.float16), True)
+
+
+def upsample_nearest2x(x):
+    """F.interpolate(x, scale_factor=2, mode="nearest") for fp16 CUDA images (NHWC is free, NCHW is converted once)."""
+    return Upsample2xFn.apply(x)

@@ -233,6 +233,22 @@ int sta_geglu_fwd(const sta_geglu_args* args, void* stream);
 int sta_geglu_bwd(const sta_geglu_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Nearest-neighbour x2 upsampling of an NHWC fp16 image (`F.interpolate(x, scale_factor=2, mode="nearest")` in
+ * Upsample.forward, ldm/modules/diffusionmodules/openaimodel.py:101-118 and model.py:42-58).
+ *   fwd: x fp16 [batch, height, width, channels] -> out fp16 [batch, 2*height, 2*width, channels]
+ *   bwd: x = d(out) fp16 [batch, 2*height, 2*width, channels] -> out = d(x) fp16 [batch, height, width, channels]
+ * (height / width are ALWAYS those of the low-resolution tensor).  channels: multiple of 8.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  void* out;
+  int32_t batch, height, width, channels;
+} sta_upsample2x_args;
+
+int sta_upsample2x_fwd(const sta_upsample2x_args* args, void* stream);
+int sta_upsample2x_bwd(const sta_upsample2x_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Test hook: one tcgen05 GEMM tile with caller-supplied UMMA descriptors (tests/test_probe_gpu.py pins the
  * shared-memory/TMEM operand encodings the kernels above rely on).  Not part of the product path.
  * ------------------------------------------------------------------------------------------------------- */

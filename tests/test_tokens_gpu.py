@@ -168,3 +168,23 @@ def test_self_attention_fused_qkv_gradient_layout(b, n, h, d):
     # dq is accumulated with fp32 reduce-adds whose order differs from launch to launch: compare with a tolerance
     diff = (a.grad.float() - bq.grad.float()).abs().max().item()
     assert diff <= 2e-3 * bq.grad.float().abs().max().item(), diff
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 1280, 8, 8), (2, 640, 32, 32), (1, 512, 64, 64), (3, 16, 5, 7)], ids=str)
+def test_upsample_nearest2x_fwd_bwd(shape):
+    """sta_upsample2x_fwd/bwd == F.interpolate(scale_factor=2, nearest) and its autograd (exact forward; the backward
+    sums four fp16 values in fp32 and rounds once)."""
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).half()
+    dy = torch.randn(shape[0], shape[1], 2 * shape[2], 2 * shape[3], generator=g).half()
+    xf = x.float().requires_grad_(True)
+    ref = F.interpolate(xf, scale_factor=2, mode="nearest")
+    ref.backward(dy.float())
+    xd = x.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
+    y = ops.upsample_nearest2x(xd)
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    assert torch.equal(y.float().cpu(), ref.detach())
+    _close(xd.grad, xf.grad, 2e-3, 2e-3, "d_x")
