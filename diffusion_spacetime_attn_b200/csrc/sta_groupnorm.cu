@@ -28,6 +28,7 @@ struct GnParams {
   const __half* x;    // [B, HW, C] (NHWC)
   const __half* dy;   // backward only
   const __half* xb;   // optional fp16 [B, C]: added to x before everything else (conv bias + timestep embedding)
+  long long xb_stride;  // elements between the rows of xb (>= C)
   const float* gamma;
   const float* beta;
   __half* out;        // y (forward) or dx (backward)
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(GnParams p) {
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (m.active) {
     float xb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.c + m.c0), xb);
+    if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.xb_stride + m.c0), xb);
     const int r0 = blockIdx.x * p.rows_per_block, r1 = min(p.hw, r0 + p.rows_per_block);
     const __half* base = p.x + ((long long)b * p.hw) * p.c + m.c0;
     for (int r = r0 + m.lane; r < r1; r += kGnUnroll * m.lanes) {
@@ -169,7 +170,7 @@ __device__ __forceinline__ void gn_load_chan(const GnParams& p, const GnMap& m, 
   load8(p.beta + m.c0, k.bet);
 #pragma unroll
   for (int i = 0; i < 8; ++i) k.shx[i] = 0.f;
-  if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.c + m.c0), k.shx);
+  if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.xb_stride + m.c0), k.shx);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int g = (m.c0 + i) / cg;
@@ -354,6 +355,7 @@ struct GnClusterParams {
   const __half* x;
   const __half* dy;
   const __half* xb;
+  long long xb_stride;
   const float* gamma;
   const float* beta;
   __half* out;
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(352) gn_cluster_fwd_kernel(GnClusterParams p) 
   {
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (active) {
-      if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.c + ch0), xb);
+      if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.xb_stride + ch0), xb);
 #pragma unroll
       for (int u = 0; u < R; ++u) {
         const int rr = r0 + lane_row + u * p.lanes;
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(640) gn_cluster_bwd_kernel(GnClusterParams p) 
       load8(p.beta + ch0, bet);
 #pragma unroll
       for (int i = 0; i < 8; ++i) sh[i] = 0.f;
-      if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.c + ch0), sh);
+      if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.xb_stride + ch0), sh);
       {
         const float* st = p.stats + ((long long)b * kGnGroups + g0 + gl0) * 2;
         const float mean_lo = st[0] * inv_n;
@@ -640,6 +642,7 @@ static int gn_cluster(const sta_groupnorm_args* a, bool bwd, cudaStream_t s, boo
   p.x = reinterpret_cast<const __half*>(a->x);
   p.dy = reinterpret_cast<const __half*>(a->d_out);
   p.xb = reinterpret_cast<const __half*>(a->x_bias);
+  p.xb_stride = a->x_bias_stride > 0 ? a->x_bias_stride : a->channels;
   p.gamma = a->gamma; p.beta = a->beta;
   p.out = reinterpret_cast<__half*>(a->out);
   p.stats = a->stats; p.bstats = a->bwd_stats;
@@ -673,6 +676,9 @@ extern "C" int sta_groupnorm_fwd(const sta_groupnorm_args* a, void* stream) {
   using namespace sta;
   if (!a || !a->x || !a->out || !a->gamma || !a->beta || !a->stats) return fail(STA_ERR_BAD_ARG, "sta_groupnorm_fwd: null pointer");
   if (a->batch < 1 || a->hw < 1) return fail(STA_ERR_BAD_ARG, "sta_groupnorm_fwd: empty shape");
+  if (a->x_bias && (a->x_bias_stride < 0 || a->x_bias_stride % 8 || (a->x_bias_stride > 0 && a->x_bias_stride < a->channels) ||
+                    (reinterpret_cast<uintptr_t>(a->x_bias) & 15u)))
+    return fail(STA_ERR_BAD_ARG, "sta_groupnorm_fwd: x_bias must be 16-byte aligned with a row stride that is 0 or a multiple of 8 >= channels");
   GnLaunch L;
   int rc = gn_launch_shape(a, &L);
   if (rc) return rc;
@@ -681,6 +687,7 @@ extern "C" int sta_groupnorm_fwd(const sta_groupnorm_args* a, void* stream) {
   p.x = reinterpret_cast<const __half*>(a->x);
   p.out = reinterpret_cast<__half*>(a->out);
   p.xb = reinterpret_cast<const __half*>(a->x_bias);
+  p.xb_stride = a->x_bias_stride > 0 ? a->x_bias_stride : a->channels;
   p.gamma = a->gamma; p.beta = a->beta; p.stats = a->stats;
   p.batch = a->batch; p.hw = a->hw; p.c = a->channels; p.rows_per_block = L.rows_per_block; p.silu = a->silu;
   p.lanes = L.lanes; p.eps = a->eps;
@@ -709,6 +716,7 @@ extern "C" int sta_groupnorm_bwd(const sta_groupnorm_args* a, void* stream) {
   p.dy = reinterpret_cast<const __half*>(a->d_out);
   p.out = reinterpret_cast<__half*>(a->out);
   p.xb = reinterpret_cast<const __half*>(a->x_bias);
+  p.xb_stride = a->x_bias_stride > 0 ? a->x_bias_stride : a->channels;
   p.gamma = a->gamma; p.beta = a->beta; p.stats = a->stats; p.bstats = a->bwd_stats;
   p.batch = a->batch; p.hw = a->hw; p.c = a->channels; p.rows_per_block = L.rows_per_block; p.silu = a->silu;
   p.lanes = L.lanes; p.eps = a->eps;

@@ -125,11 +125,18 @@ class ResBlock(TimestepBlock):
                                   n1.eps, True)
         with th.autocast("cuda", enabled=False):
             h = F.conv2d(g1, cached_sum(self, "w1", [conv1.weight], f16), None, conv1.stride, conv1.padding)
-            act = getattr(emb, "_sta_silu", None)  # SiLU(emb) is shared by all 22 ResBlocks (UNetModel.forward)
-            if act is None:
-                act = F.silu(emb)
-            xb = F.linear(act if act.dtype == f16 else act.to(f16), cached_sum(self, "we", [emb_lin.weight], f16),
-                          cached_sum(self, "be", [emb_lin.bias, conv1.bias], f16))
+            # x_bias = emb_layers(emb) + conv1.bias.  UNetModel.forward hands over one [B, sum C] gather from its
+            # per-timestep table (a strided column slice is this block's vector); standalone blocks project themselves
+            slot = getattr(emb, "_sta_xb", None)
+            if slot is not None and id(self) in slot[1]:
+                off = slot[1][id(self)]
+                xb = slot[0][:, off:off + self.out_channels]
+            else:
+                act = getattr(emb, "_sta_silu", None)  # SiLU(emb) is shared by all ResBlocks
+                if act is None:
+                    act = F.silu(emb)
+                xb = F.linear(act if act.dtype == f16 else act.to(f16), cached_sum(self, "we", [emb_lin.weight], f16),
+                              cached_sum(self, "be", [emb_lin.bias, conv1.bias], f16))
             g2 = _ops.group_norm_silu(h, cached_sum(self, "g2", [n2.weight], f32), cached_sum(self, "b2", [n2.bias], f32),
                                       n2.eps, True, x_bias=xb)
             h = F.conv2d(g2, cached_sum(self, "w2", [conv2.weight], f16), None, conv2.stride, conv2.padding)
@@ -164,6 +171,8 @@ class ResBlock(TimestepBlock):
 
 
 class UNetModel(nn.Module):
+    XB_TABLE_STEPS = 1000  # DDPM training timesteps (v1-inference.yaml:8); sampler timesteps are always below it
+
     def __init__(self, image_size=32, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2,
                  attention_resolutions=(4, 2, 1), dropout=0, channel_mult=(1, 2, 4, 4), conv_resample=True, dims=2,
                  num_classes=None, use_checkpoint=False, use_fp16=False, num_heads=8, num_head_channels=-1,
@@ -242,6 +251,37 @@ class UNetModel(nn.Module):
                 m.checkpoint = bool(flag)
                 m.checkpoint_min_tokens = int(min_tokens)
 
+    # -- per-timestep ResBlock biases ---------------------------------------------------------------------------
+    def _timestep_bias(self, timesteps):
+        """([B, sum C] fp16, {id(ResBlock): column offset}): `emb_layers(time_embed(t)) + conv1.bias` of EVERY ResBlock for
+        the given integer timesteps, gathered from a table over all `XB_TABLE_STEPS` timesteps.  The UNet is frozen while
+        sampling, so the 22 per-block projections of an evaluation (22 tiny GEMMs = 22 graph nodes) collapse into one row
+        gather; the table (1000 x 20160 fp16 = 40 MB for SD-v1) is one GEMM, rebuilt only when a weight changes."""
+        blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+        params = [p for p in self.time_embed.parameters()]
+        for rb in blocks:
+            params += [rb.emb_layers[1].weight, rb.emb_layers[1].bias, rb.in_layers[2].bias]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        cache = self.__dict__.get("_xb_cache")
+        if cache is None or cache[0] != key:
+            f16 = th.float16
+            dev = timesteps.device
+            with th.no_grad(), th.autocast("cuda", enabled=False):
+                t = th.arange(self.XB_TABLE_STEPS, device=dev)
+                e = timestep_embedding(t, self.model_channels, repeat_only=False).to(f16)
+                l0, l2 = self.time_embed[0], self.time_embed[2]
+                e = F.linear(F.silu(F.linear(e, l0.weight.to(f16), l0.bias.to(f16))), l2.weight.to(f16), l2.bias.to(f16))
+                w_all = th.cat([rb.emb_layers[1].weight.to(f16) for rb in blocks])
+                b_all = th.cat([(rb.emb_layers[1].bias.float() + rb.in_layers[2].bias.float()).to(f16) for rb in blocks])
+                table = F.linear(F.silu(e), w_all, b_all).contiguous()
+            offs, off = {}, 0
+            for rb in blocks:
+                offs[id(rb)] = off
+                off += rb.out_channels
+            cache = (key, table, offs)
+            self.__dict__["_xb_cache"] = cache
+        return cache[1].index_select(0, timesteps), cache[2]
+
     # -- per-prompt attention state (in-memory replacement of the reference's c{i}_*.pt files) ---------------
     def transformer_blocks(self) -> Iterable[BasicTransformerBlock]:
         for m in self.modules():
@@ -265,7 +305,10 @@ class UNetModel(nn.Module):
         hs = []
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels, repeat_only=False))
         if not emb.requires_grad:
-            emb._sta_silu = F.silu(emb)  # every ResBlock starts its embedding branch with the same SiLU (:217-223)
+            if emb.is_cuda and timesteps.is_cuda and timesteps.dtype == th.long and _frozen(self):
+                emb._sta_xb = self._timestep_bias(timesteps)
+            else:
+                emb._sta_silu = F.silu(emb)  # every ResBlock starts its embedding branch with the same SiLU (:217-223)
         # the reference hands timesteps[0] (a device scalar) to every block, which then syncs on `time == 981`
         # (attention.py:240); callers of this package pass the same value as a host int instead
         time = step_time if step_time is not None else int(timesteps[0].item())  # one sync instead of 16

@@ -330,12 +330,17 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
 
 
 def _check_x_bias(x_bias, b: int, c: int):
+    """(pointer, row stride) of an fp16 [b, c] bias whose rows are dense; the rows themselves may be strided (a column slice
+    of a wider table)."""
     if x_bias is None:
-        return None
+        return None, 0
     _require(x_bias, "x_bias")
-    if tuple(x_bias.shape) != (b, c) or not x_bias.is_contiguous():
-        raise RuntimeError(f"x_bias must be a contiguous fp16 [{b}, {c}] tensor, got {tuple(x_bias.shape)}")
-    return x_bias.data_ptr()
+    if tuple(x_bias.shape) != (b, c) or x_bias.stride(1) != 1 or (b > 1 and (x_bias.stride(0) < c or x_bias.stride(0) % 8)):
+        raise RuntimeError(f"x_bias must be fp16 [{b}, {c}] with dense rows and a row stride that is a multiple of 8, got "
+                           f"{tuple(x_bias.shape)} / {tuple(x_bias.stride())}")
+    if x_bias.data_ptr() % 16:
+        raise RuntimeError("x_bias must be 16-byte aligned")
+    return x_bias.data_ptr(), (x_bias.stride(0) if b > 1 else c)
 
 
 def groupnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
@@ -350,7 +355,7 @@ def groupnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     a = native.GroupNormArgs()
     a.x, a.gamma, a.beta, a.out, a.stats = x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), stats.data_ptr()
     a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
-    a.x_bias = _check_x_bias(x_bias, b, c)
+    a.x_bias, a.x_bias_stride = _check_x_bias(x_bias, b, c)
     with _timed("groupnorm_fwd", (b, h * w, c)):
         native.check(native.load().sta_groupnorm_fwd(C.byref(a), _stream()), "sta_groupnorm_fwd")
     LAUNCHES["groupnorm_fwd"] += 2
@@ -366,7 +371,7 @@ def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool, x_bias: 
     a.x, a.d_out, a.gamma, a.beta, a.out = x.data_ptr(), d_out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), d_x.data_ptr()
     a.stats, a.bwd_stats = stats.data_ptr(), bstats.data_ptr()
     a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
-    a.x_bias = _check_x_bias(x_bias, b, c)
+    a.x_bias, a.x_bias_stride = _check_x_bias(x_bias, b, c)
     with _timed("groupnorm_bwd", (b, h * w, c)):
         native.check(native.load().sta_groupnorm_bwd(C.byref(a), _stream()), "sta_groupnorm_bwd")
     LAUNCHES["groupnorm_bwd"] += 2

@@ -168,6 +168,8 @@ typedef struct {
    * conv bias + projected timestep embedding (openaimodel.py:259-268).  NULL = none.  The backward needs the same
    * values again (it normalises x + x_bias); no gradient is produced for x_bias. */
   const void* x_bias;
+  int64_t x_bias_stride; /* elements between the rows of x_bias; 0 = channels (dense).  A larger stride lets x_bias be a
+                          * column slice of one [batch, sum of channels] table shared by all ResBlocks. */
 } sta_groupnorm_args;
 
 int sta_groupnorm_fwd(const sta_groupnorm_args* args, void* stream);

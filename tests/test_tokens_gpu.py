@@ -141,7 +141,10 @@ def test_groupnorm_with_channel_bias(shape, silu):
         ref = F.silu(ref)
     (ref * dy.float()).sum().backward()
     xd = x.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
-    y = ops.group_norm_silu(xd, gamma.cuda(), beta.cuda(), 1e-5, silu, x_bias=xb.cuda())
+    # the bias is handed over as a column slice of a wider table (row stride c + 64), as UNetModel does
+    table = torch.zeros(b, c + 64, dtype=torch.float16, device="cuda")
+    table[:, 32:32 + c] = xb.cuda()
+    y = ops.group_norm_silu(xd, gamma.cuda(), beta.cuda(), 1e-5, silu, x_bias=table[:, 32:32 + c])
     y.backward(dy.cuda())
     torch.cuda.synchronize()
     assert native.device_error() == 0
