@@ -157,3 +157,31 @@ def test_clip_global_loss_accepts_non_512_images():
     for size in (512, 768, 100):  # 100: no integer window -> bilinear resize
         out = loss.forward_2(torch.rand(3, size, size, generator=g), "a red cube")
         assert out.shape == (1,) and bool(torch.isfinite(out).all())
+
+
+def test_timestep_bias_table_matches_per_block_projection():
+    """UNetModel._timestep_bias: row t of the table == emb_layers(time_embed(timestep_embedding(t))) + conv1.bias of every
+    ResBlock (openaimodel.py:217-223,259-268), computed the ordinary way in fp32 (the table is fp16)."""
+    import torch.nn.functional as F
+
+    from diffusion_spacetime_attn_b200.ldm.modules.diffusionmodules.openaimodel import ResBlock, UNetModel
+    from diffusion_spacetime_attn_b200.ldm.modules.diffusionmodules.util import timestep_embedding
+
+    torch.manual_seed(0)
+    m = UNetModel(attention_resolutions=(1,), num_res_blocks=1, channel_mult=(1, 2), model_channels=32, num_heads=4,
+                  context_dim=16).eval().requires_grad_(False)
+    for p in m.parameters():  # zero-initialised convs / random biases: make every term visible
+        if p.dim() == 1:
+            p.copy_(torch.randn_like(p) * 0.3)
+    m.XB_TABLE_STEPS = 64
+    t = torch.tensor([3, 41], dtype=torch.long)
+    xb, offs = m._timestep_bias(t)
+    blocks = [b for b in m.modules() if isinstance(b, ResBlock)]
+    assert xb.shape == (2, sum(b.out_channels for b in blocks)) and xb.dtype == torch.float16
+    emb = m.time_embed(timestep_embedding(t, m.model_channels))
+    for b in blocks:
+        ref = b.emb_layers(emb) + b.in_layers[2].bias
+        got = xb[:, offs[id(b)]:offs[id(b)] + b.out_channels].float()
+        assert (got - ref).abs().max().item() < 2e-2 * (1 + ref.abs().max().item())
+    again, _ = m._timestep_bias(t)
+    assert again.data_ptr() != xb.data_ptr() and m.__dict__["_xb_cache"][1].shape[0] == 64  # cached table, fresh gather
