@@ -60,7 +60,10 @@ def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
 
 @pytest.mark.parametrize("struct,cname", [("SattnFwdArgs", "sta_sattn_fwd_args"), ("SattnBwdArgs", "sta_sattn_bwd_args"),
                                           ("XattnFwdArgs", "sta_xattn_fwd_args"), ("XattnBwdArgs", "sta_xattn_bwd_args"),
-                                          ("ProbeArgs", "sta_probe_args"), ("GroupNormArgs", "sta_groupnorm_args")])
+                                          ("ProbeArgs", "sta_probe_args"), ("GroupNormArgs", "sta_groupnorm_args"),
+                                          ("AddLayerNormArgs", "sta_add_layernorm_args"),
+                                          ("AddLayerNormBwdArgs", "sta_add_layernorm_bwd_args"),
+                                          ("GegluArgs", "sta_geglu_args"), ("Upsample2xArgs", "sta_upsample2x_args")])
 def test_ctypes_structs_mirror_the_header(struct, cname):
     from diffusion_spacetime_attn_b200 import native
 
@@ -75,6 +78,41 @@ def test_ctypes_structs_mirror_the_header(struct, cname):
         for part in decl.split(","):
             names.append(re.sub(r"\[.*\]", "", part).replace("*", "").strip())
     assert names == [f[0] for f in getattr(native, struct)._fields_]
+
+
+STRUCTS = {"SattnFwdArgs": "sta_sattn_fwd_args", "SattnBwdArgs": "sta_sattn_bwd_args", "XattnFwdArgs": "sta_xattn_fwd_args",
+           "XattnBwdArgs": "sta_xattn_bwd_args", "GroupNormArgs": "sta_groupnorm_args", "ProbeArgs": "sta_probe_args",
+           "AddLayerNormArgs": "sta_add_layernorm_args", "AddLayerNormBwdArgs": "sta_add_layernorm_bwd_args",
+           "GegluArgs": "sta_geglu_args", "Upsample2xArgs": "sta_upsample2x_args"}
+
+
+def test_ctypes_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
+    """Field NAMES can agree while the layout drifts (a float followed by an int64 is padded): compile the header with gcc
+    and compare sizeof / offsetof of every field with ctypes."""
+    import shutil
+    import subprocess
+
+    from diffusion_spacetime_attn_b200 import native
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "sta_b200.h"}"', "int main(void) {"]
+    for py, cname in STRUCTS.items():
+        lines.append(f'  printf("{py} size %zu\\n", sizeof({cname}));')
+        for fname, _ in getattr(native, py)._fields_:
+            lines.append(f'  printf("{py} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.splitlines():
+        py, field, value = line.split()
+        st = getattr(native, py)
+        got = ctypes.sizeof(st) if field == "size" else getattr(st, field).offset
+        assert got == int(value), f"{py}.{field}: ctypes {got} != C {value}"
 
 
 def test_ops_refuse_cpu_tensors():
