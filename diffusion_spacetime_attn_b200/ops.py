@@ -14,7 +14,7 @@ from . import native
 
 # number of kernels launched by this module since import (bench.py reports it as `gpu_launches`)
 LAUNCHES = {"sattn_fwd": 0, "sattn_bwd": 0, "xattn_fwd": 0, "xattn_bwd": 0, "groupnorm_fwd": 0, "groupnorm_bwd": 0,
-            "add_layernorm_fwd": 0, "add_layernorm_bwd": 0, "geglu_fwd": 0, "geglu_bwd": 0, "bias_add": 0,
+            "add_layernorm_fwd": 0, "add_layernorm_bwd": 0, "geglu_fwd": 0, "geglu_bwd": 0,
             "upsample2x_fwd": 0, "upsample2x_bwd": 0}
 
 
