@@ -52,9 +52,12 @@ class GraphedUNetEval:
     """Captured graphs of `unet` for a fixed (batch, n_obj, latent) signature."""
 
     def __init__(self, unet, batch2: int, n_obj: int, latent_hw: Tuple[int, int], ctx_shape=(77, 768), warmup: int = 2,
-                 pools: Optional[list] = None, max_slots: int = 0, reserve_bytes: int = 24 << 30):
+                 pools: Optional[list] = None, max_slots: int = 0, reserve_bytes: int = 24 << 30,
+                 pool_bytes: Optional[list] = None):
         self.unet = unet
         self.pools = pools if pools is not None else []   # shared with the other signatures of the runner
+        self.pool_bytes = pool_bytes if pool_bytes is not None else []  # bytes reserved by each pool so far (all signatures)
+        self.first_growth: Optional[int] = None  # what THIS signature's first slot added to its pool
         self.max_slots = max_slots
         self.reserve_bytes = reserve_bytes
         self.slots: List[_Slot] = []
@@ -135,15 +138,23 @@ class GraphedUNetEval:
         if k >= self.max_slots:
             return None
         free, _ = torch.cuda.mem_get_info()
-        need = self.slot_bytes if self.slot_bytes else (4 << 30)
-        if k >= len(self.pools) and free < self.reserve_bytes + need:  # a NEW pool would not fit next to the VAE / CLIP pass
+        new_pool = k >= len(self.pools)
+        if self.first_growth is None:   # first slot of this signature: nothing measured yet
+            need = (4 << 30) if new_pool else 0
+        elif new_pool:                  # a whole new pool: as large as the ones this signature already filled
+            need = max(self.pool_bytes) if self.pool_bytes else self.first_growth
+        else:                           # an existing pool (sized by another signature) grows as the first one did
+            need = self.first_growth
+        if free < self.reserve_bytes + need:  # would not fit next to the VAE / CLIP pass: recompute from here on
             self.max_slots = k
             return None
-        if k >= len(self.pools):
+        if new_pool:
             self.pools.append(torch.cuda.graph_pool_handle())
+            self.pool_bytes.append(0)
         pool = self.pools[k]
         slot = _Slot()
         torch.cuda.synchronize()
+        torch.cuda.empty_cache()  # (torch.cuda.graph does this on entry anyway; doing it first keeps the delta honest)
         before = torch.cuda.memory_reserved()
         with torch.enable_grad():
             xg = self.x.detach().requires_grad_(True)   # views of the static input buffers
@@ -165,8 +176,11 @@ class GraphedUNetEval:
         slot.eps, slot.dx = eps.detach(), grads[0]
         slot.dcoef = grads[1] if self.n_obj else None
         torch.cuda.synchronize()
-        if not self.slot_bytes:
-            self.slot_bytes = max(torch.cuda.memory_reserved() - before, 1 << 20)
+        grown = max(torch.cuda.memory_reserved() - before, 0)
+        self.pool_bytes[k] += grown
+        if self.first_growth is None:
+            self.first_growth = grown
+        self.slot_bytes = max(self.slot_bytes, self.pool_bytes[k])  # footprint of one retained evaluation (reported)
         self.slots.append(slot)
         return slot
 
@@ -274,6 +288,7 @@ class GraphedModelRunner:
         self.max_slots = int(os.environ.get("STA_MAX_SLOTS", "64")) if max_slots is None else int(max_slots)
         self.reserve_bytes = int(float(os.environ.get("STA_SLOT_RESERVE_GIB", "24") if reserve_gib is None else reserve_gib) * 2 ** 30)
         self.pools: list = []
+        self.pool_bytes: list = []
 
     def begin_prompt(self, x_shape, context, local_contexts, bboxes, first_timestep: int) -> None:
         """Refresh the static per-prompt state (context K/V caches, masks) and select / capture the graph."""
@@ -286,7 +301,7 @@ class GraphedModelRunner:
         fresh = g is None
         if fresh:
             g = GraphedUNetEval(unet, batch2, n_obj, (x_shape[2], x_shape[3]), tuple(context.shape[1:]), pools=self.pools,
-                                max_slots=self.max_slots, reserve_bytes=self.reserve_bytes)
+                                max_slots=self.max_slots, reserve_bytes=self.reserve_bytes, pool_bytes=self.pool_bytes)
         g.set_context(context)
         g.bboxes = bboxes
         # (re)build every block's cache in place from the new context / local embeddings / layout
