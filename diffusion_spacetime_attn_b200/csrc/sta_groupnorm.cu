@@ -38,10 +38,12 @@ struct GnParams {
   float eps;
 };
 
-__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+// __fdividef: 2 instructions instead of the ~10 of an IEEE division (these kernels are instruction-bound, ncu: 36
+// thread-instructions per element in the forward); its 2-ulp error is far below the fp16 rounding of the result
+__device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.f + __expf(-z)); }
 __device__ __forceinline__ float dsilu_f(float z) {
-  const float s = 1.f / (1.f + __expf(-z));
-  return s * (1.f + z * (1.f - s));
+  const float s = __fdividef(1.f, 1.f + __expf(-z));
+  return s * fmaf(z, 1.f - s, 1.f);
 }
 
 // thread -> (row lane, 8-channel vector); threads beyond vecs * lanes (warp padding) only help in the reductions
