@@ -17,7 +17,8 @@ sharded round-robin, no data-path collective (weights broadcast once at start-up
 `roofline` the kernel with the largest share of device time inside the timed region, timed per launch with CUDA
            events on the launching stream; achieved = algorithmic FLOPs per launch / mean launch time; peak = the
            driver-measured MEASURED_PEAKS.json figure (sustained: the kernel runs inside a long step).
-`cpu_baseline` the CPU oracle (a port of the reference algorithm) timed on this box's host cores on a bounded sample.
+`cpu_baseline` the CPU oracle (a port of the reference algorithm) timed on this box's host cores on a bounded sample
+           (forward and forward+backward UNet evaluations, extrapolated to one alpha-optimised image).
 """
 from __future__ import annotations
 
@@ -195,10 +196,12 @@ def standalone_kernel_ms(kind, key, iters=10):
 # CPU oracle timing (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------------
 def cpu_oracle_images_per_sec(n_evals: int):
-    """Time `n_evals` forward UNet evaluations of the CPU oracle (fp32, all host threads) at BASELINE configs[1]'s
-    geometry (batch 2 CFG, 64x64 latent, 2 objects) and extrapolate to images/s = 1 / (153 evals x t_eval).
-    The reference cannot run its backward on CPU (in-place hazard), so this is forward-only work and
-    therefore an UPPER bound on the CPU throughput of the full alpha-optimised image."""
+    """Time the CPU oracle (fp32, all host threads) at BASELINE configs[1]'s geometry (batch 2 CFG, 64x64 latent, 2 objects)
+    on a bounded sample — `n_evals` forward UNet evaluations and `n_evals` forward+backward evaluations (gradients w.r.t.
+    the latent and alpha, torch autograd through the out-of-place restatement; the reference itself cannot back-propagate
+    on CPU) — and extrapolate one alpha-optimised image = 3 x 51 forwards + 3 x 50 backwards, WITHOUT the
+    reference's per-block recompute (the favourable reading for the CPU):  t_image = 153 t_fwd + 150 (t_fwd+bwd - t_fwd).
+    Returns (images/s, t_fwd, t_fwd+bwd, cores)."""
     import torch
 
     from oracle import sta_oracle as O
@@ -220,27 +223,39 @@ def cpu_oracle_images_per_sec(n_evals: int):
     x = torch.randn(2, 4, 64, 64, generator=g)
     ctx = torch.randn(2, 77, 768, generator=g)
     locs = [torch.randn(2, 77, 768, generator=g) for _ in range(2)]
-    coef = torch.tensor([2.5, 2.5])
     bboxes = [[0.3, 0.5], [0.7, 0.5]]
     t_in = torch.full((2,), 501, dtype=torch.long)
     with torch.no_grad():
-        O.unet_forward(x, t_in, ctx, coef, bboxes, locs, p, cfg)  # warm-up
+        O.unet_forward(x, t_in, ctx, torch.tensor([2.5, 2.5]), bboxes, locs, p, cfg)  # warm-up
         t0 = time.perf_counter()
         for _ in range(n_evals):
-            O.unet_forward(x, t_in, ctx, coef, bboxes, locs, p, cfg)
-        dt = (time.perf_counter() - t0) / n_evals
-    return 1.0 / (EVALS_PER_IMAGE * dt), dt, cores
+            O.unet_forward(x, t_in, ctx, torch.tensor([2.5, 2.5]), bboxes, locs, p, cfg)
+        t_f = (time.perf_counter() - t0) / n_evals
+    t0 = time.perf_counter()
+    for _ in range(n_evals):
+        xg = x.clone().requires_grad_(True)
+        coef = torch.tensor([2.5, 2.5], requires_grad=True)
+        y = O.unet_forward(xg, t_in, ctx, coef, bboxes, locs, p, cfg)
+        torch.autograd.grad(y, [xg, coef], torch.ones_like(y))
+    t_fb = (time.perf_counter() - t0) / n_evals
+    t_image = EVALS_PER_IMAGE * t_f + 3 * 50 * max(t_fb - t_f, 0.0)
+    return 1.0 / t_image, t_f, t_fb, cores
+
+
+def _cpu_sample_text(n, t_f, t_fb):
+    return (f"{n} forward and {n} forward+backward UNet evaluation(s) of the CPU oracle (fp32, batch 2, 64x64 latent, 2 objects): "
+            f"{t_f:.2f} s and {t_fb:.2f} s each; one alpha-optimised image extrapolated as 153 t_fwd + 150 (t_fwd+bwd - t_fwd), "
+            "no per-block recompute (the reference has no working CPU backward; this is the oracle port's autograd)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = 1  # one forward UNet evaluation per "step" (bounded sample of one image's 153 evaluations)
+    per_step = 1  # one forward + one forward/backward UNet evaluation per "step" (bounded sample of an image's 153 + 150)
     n = max(1, args.steps) * per_step
-    ips, dt, cores = cpu_oracle_images_per_sec(n)
-    sample = (f"{n} forward UNet evaluation(s) of the CPU oracle (fp32, batch 2, 64x64 latent, 2 objects), "
-              f"{dt:.2f} s each; images/s extrapolated as 1/(153 x t_eval), forward-only (the reference has no CPU backward)")
+    ips, t_f, t_fb, cores = cpu_oracle_images_per_sec(n)
+    sample = _cpu_sample_text(n, t_f, t_fb)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak",
@@ -417,11 +432,9 @@ def run_native(args):
             "device_error": err,
         }
         if world == 1 and not args.no_cpu_baseline:
-            ips, dt, cores = cpu_oracle_images_per_sec(2)
-            line["cpu_baseline"] = {
-                "value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"2 forward UNet evaluations of the CPU oracle (fp32, batch 2, 64x64, 2 objects), {dt:.2f} s each; "
-                          "extrapolated as 1/(153 x t_eval), forward-only (the reference has no CPU backward)"}
+            ips, t_f, t_fb, cores = cpu_oracle_images_per_sec(1)
+            line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": _cpu_sample_text(1, t_f, t_fb)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
