@@ -253,7 +253,7 @@ def run_reference(args):
     if rank != 0:
         return
     per_step = 1  # one forward + one forward/backward UNet evaluation per "step" (bounded sample of an image's 153 + 150)
-    n = max(1, args.steps) * per_step
+    n = min(max(1, args.steps), 6) * per_step  # bounded: ~8 s per step on 16 host cores, the run must end within minutes
     ips, t_f, t_fb, cores = cpu_oracle_images_per_sec(n)
     sample = _cpu_sample_text(n, t_f, t_fb)
     line = {
