@@ -172,7 +172,7 @@ def standalone_kernel_ms(kind, key, iters=10):
             coef = torch.full((B, n_obj), 2.5, device="cuda")
         out, lse = ops.xattn_fwd(q, kc, vc, mask, coef, h)
         fn = (lambda: ops.xattn_fwd(q, kc, vc, mask, coef, h)) if kind == "xattn_fwd" else (
-            lambda: ops.xattn_bwd(q, kc, vc, mask, coef, lse, do, h))
+            lambda: ops.xattn_bwd(q, kc, vc, mask, coef, lse, do, h, out=out))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(3):
         fn()

@@ -7,6 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/sta_b200.h"  // return codes STA_OK / STA_ERR_*
 
 namespace sta {
@@ -21,6 +24,29 @@ int fail(int code, const char* fmt, ...);
     cudaError_t _e = (expr);                                                                 \
     if (_e != cudaSuccess) return ::sta::fail(STA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
+
+// Runs `f` (a cudaError_t-returning callable, e.g. cudaFuncSetAttribute for a kernel's dynamic shared memory) once per
+// DEVICE, thread-safely: function attributes are per device, and the launchers may be called from several host threads.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> done[4];  // one bit per device ordinal (256 devices)
+  std::mutex mu;
+  PerDeviceOnce() { for (auto& d : done) d.store(0); }
+  template <typename F>
+  int run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(STA_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    const int w = (dev >> 6) & 3;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done[w].load(std::memory_order_acquire) & bit) return STA_OK;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[w].load(std::memory_order_acquire) & bit) return STA_OK;
+    e = f();
+    if (e != cudaSuccess) return fail(STA_ERR_CUDA, "per-device kernel attribute: %s", cudaGetErrorString(e));
+    done[w].fetch_or(bit, std::memory_order_release);
+    return STA_OK;
+  }
+};
 
 // one 4-byte device word per process that kernels bump on an mbarrier timeout (never freed)
 unsigned int* device_error_word();

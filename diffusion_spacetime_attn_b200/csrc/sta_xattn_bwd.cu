@@ -7,13 +7,20 @@
 //     dA_u = dO_u - sigma dO_c,  dA_g = dO_c,  dA_i = w_i dO_c,      sigma = sum_i w_i
 //     dS_x = P_x o (dA_x V_x^T - rowsum(P_x o dA_x V_x^T)),  dQ = scale * sum_x dS_x K_x
 //     dc_i = sum_pix m_i <dO_c, A_i - A_u> = sum_pix m_i (delta_i - delta_uc),
-//            delta_x = rowsum(P_x o dO_c V_x^T)   (flash-attention's delta term, so A_i is never rebuilt)
+//            delta_i  = rowsum(P_i o dO_c V_i^T)   (flash-attention's delta term, so A_i is never rebuilt)
+//            delta_uc = <dO_c, A_u> = <dO_c, out_u>  (the forward's unconditional output IS A_u)
 //
-// CTA = one 128-pixel tile of one (prompt, head); 6 warps: TMA producer, MMA issuer, 4 warps with one thread per
-// pixel row.  Tile 0 is the unconditional row (three accumulators: S_u, dO_u V^T, dO_c V^T), tiles 1.. are the
-// conditional row's contexts (objects whose mask is empty in this pixel tile are skipped, as in the forward).
-// TMEM: four 80-column slots (S/dP pairs A and B, double-buffered across tiles) + the dQ accumulator at 320.
-// P is recomputed from the forward's LSE; dS is written back over S as packed fp16 and consumed from TMEM.
+// Round-2 layout (latency-bound op, see sta_xattn_fwd.cu): CTA = one 128-pixel tile of one (prompt, head);
+//   warp 0       control: barrier init, every TMA load, MMA issue, ring refills
+//   warps 1..4   math warpgroup 0 (one thread per pixel row)      warps 5..8  math warpgroup 1 (when NBUF == 2)
+// Task 0 = unconditional row, tasks 1.. = conditional row's contexts (global, then the objects whose mask is
+// non-empty in this tile).  Task t uses TMEM buffer t % NBUF = [S | dP] (2 x 80 columns) and warpgroup t % NBUF:
+//   control: S_t = Q K_t^T, dP_t = dA V_t^T (SS)  ->  math: P from the forward's LSE, delta, dS -> packed fp16 over S
+//   control: dQ (+)= dS_t K_t (TS, K MN-major)    ->  math: store dQ_u after task 0, dQ_c after the last task
+// dA_u = dO_u - sigma dO_c is formed ONCE in shared memory (fp16, in place over the dO_u tile) by warpgroup 0, so the
+// unconditional task is an ordinary task (no third accumulator): head dim 40 needs 160 + 2 x 48 = 256 TMEM columns
+// and two CTAs are resident per SM; head dims 80 / 160 run one CTA per SM (fewer CTAs than SMs at those levels).
+// P is evaluated once per score (kept in registers between the delta pass and the dS pass).
 #include "../../include/sta_b200.h"
 #include "sta_common.cuh"
 #include "sta_host.h"
@@ -28,45 +35,55 @@ template <int D>
 struct XattnBwdCfg {
   static constexpr int DMMA = (D + 15) / 16 * 16;
   static constexpr int NBLK = (D + 63) / 64;
-  static constexpr int ST = (NBLK == 3) ? 1 : (NBLK == 2 ? 2 : 3);  // K+V ring depth
-  static constexpr bool PREFETCH = ST >= 2;
+  static constexpr int NBUF = (NBLK == 2) ? 2 : 1;  // [S | dP] TMEM buffers = math warpgroups
+  static constexpr int ST = (NBLK == 3) ? 1 : 2;    // K and V ring depth
+  static constexpr bool SEPQ = NBLK <= 2;           // Q_c has its own tile (else it re-uses Q_u's once S_u is done)
   static constexpr int QTILE = NBLK * kBQBlockBytes;
   static constexpr int CTILE = NBLK * kBCBlockBytes;
-  static constexpr int SMEM_BYTES = 3 * QTILE + 2 * ST * CTILE + 1024;
-  static constexpr int THREADS = 192;
-  static constexpr int TMEM_DQ = 320;
+  static constexpr int NQ = SEPQ ? 4 : 3;
+  static constexpr int SMEM_BYTES = NQ * QTILE + 2 * ST * CTILE + 1024;
+  static constexpr int THREADS = 32 * (1 + 4 * NBUF);
+  static constexpr int TMEM_DQ = NBUF * 160;  // dQ_u, then dQ_c at + DMMA
+  static constexpr int TMEM_COLS = (TMEM_DQ + 2 * DMMA <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (TMEM_COLS == 256) ? 2 : 1;
+  static_assert(TMEM_DQ + 2 * DMMA <= 512, "TMEM budget");
 };
 
 struct XattnBwdParams {
   const uint8_t* mask;
   const float* coef;
-  const float* lse;  // [B, heads, 2+n_obj, n]
-  __half* d_q;       // [2B, n, heads*D] contiguous
-  float* d_coef;     // [B, n_obj]
+  const float* lse;   // [B, heads, 2+n_obj, n]
+  const __half* out;  // forward output (only the unconditional rows are read), may be null when n_obj == 0
+  __half* d_q;        // [2B, n, heads*D] contiguous
+  float* d_coef;      // [B, n_obj]
   int prompts, n, heads, n_obj, ctx_len;
+  long long o_token_stride, o_batch_stride;
   float scale, scale_log2;
   unsigned int* err;
 };
 
 template <int D>
-__global__ void __launch_bounds__(XattnBwdCfg<D>::THREADS, 1)
+__global__ void __launch_bounds__(XattnBwdCfg<D>::THREADS, XattnBwdCfg<D>::MIN_CTAS)
 xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                  const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                  const XattnBwdParams p) {
   using Cfg = XattnBwdCfg<D>;
-  constexpr int ST = Cfg::ST, NBLK = Cfg::NBLK, DMMA = Cfg::DMMA;
+  constexpr int ST = Cfg::ST, NBLK = Cfg::NBLK, DMMA = Cfg::DMMA, NBUF = Cfg::NBUF;
+  constexpr bool SEPQ = Cfg::SEPQ;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sQ = smem;                  // Q_u, later re-filled with Q_c
-  unsigned char* sDOu = sQ + Cfg::QTILE;
+  unsigned char* sQu = smem;                  // Q_u (head dim 160: re-filled with Q_c once S_u is done)
+  unsigned char* sDOu = sQu + Cfg::QTILE;     // dO_u, rewritten in place as dA_u = dO_u - sigma dO_c
   unsigned char* sDOc = sDOu + Cfg::QTILE;
-  unsigned char* sK = sDOc + Cfg::QTILE;     // ring of ST stages, each K then V
+  unsigned char* sQc = SEPQ ? sDOc + Cfg::QTILE : sQu;
+  unsigned char* sK = smem + Cfg::NQ * Cfg::QTILE;
   unsigned char* sV = sK + ST * Cfg::CTILE;
 
-  __shared__ uint64_t in_full, q2_full, qu_done, kv_full[ST], kv_empty[ST];
-  __shared__ uint64_t sdp_full[2], ds_ready, dq_full, dq_drained;
+  __shared__ uint64_t qu_full, do_full, qc_full, su_done, dau_ready;
+  __shared__ uint64_t k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
+  __shared__ uint64_t sdp_full[NBUF], ds_ready[NBUF], dqu_full, dqc_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
   __shared__ int tile_slot[2 + kBMaxObj];
@@ -77,48 +94,81 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int q0 = blockIdx.x * 128, h = blockIdx.y, pr = blockIdx.z;
   const int n = p.n, B = p.prompts, n_obj = p.n_obj, n_slots = 2 + p.n_obj;
 
-  if (tid == 0) {
-    dead = 0;
-    mbar_init(&in_full, 1);
-    mbar_init(&q2_full, 1);
-    mbar_init(&qu_done, 1);
-    for (int i = 0; i < ST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(&sdp_full[0], 1);
-    mbar_init(&sdp_full[1], 1);
-    mbar_init(&ds_ready, 4);
-    mbar_init(&dq_full, 1);
-    mbar_init(&dq_drained, 4);
-    mbar_fence_init();
-  }
-  if (tid < kBMaxObj) dcoef_s[tid] = 0.f;
-  if (warp == 1) {
-    tmem_alloc(&tmem_base_s, 512);
-    tmem_relinquish();
-  }
+  auto load_q = [&](unsigned char* dst, const CUtensorMap* tm, uint64_t* bar, int batch_row) {
+    for (int blk = 0; blk < NBLK; ++blk) tma_load_4d_w(dst + blk * kBQBlockBytes, tm, bar, blk * 64, h, q0, batch_row);
+  };
+  auto load_k = [&](int t, int slot) {
+    const int st = t % ST;
+    mbar_expect_tx_w(&k_full[st], Cfg::CTILE);
+    for (int blk = 0; blk < NBLK; ++blk)
+      tma_load_4d_w(sK + (st * NBLK + blk) * kBCBlockBytes, &tm_k, &k_full[st], blk * 64, h, 0, pr * n_slots + slot);
+  };
+  auto load_v = [&](int t, int slot) {
+    const int st = t % ST;
+    mbar_expect_tx_w(&v_full[st], Cfg::CTILE);
+    for (int blk = 0; blk < NBLK; ++blk)
+      tma_load_4d_w(sV + (st * NBLK + blk) * kBCBlockBytes, &tm_v, &v_full[st], blk * 64, h, 0, pr * n_slots + slot);
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      tma_prefetch_desc(&tm_q);
-      tma_prefetch_desc(&tm_do);
-      tma_prefetch_desc(&tm_k);
-      tma_prefetch_desc(&tm_v);
-      tile_slot[0] = 0;
-      tile_slot[1] = 1;
-    }
-    int cnt = 2;
-    for (int i = 0; i < n_obj; ++i) {
-      const uint8_t* m = p.mask + ((long long)pr * n_obj + i) * n + q0;
-      int any = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int px = lane * 4 + j;
-        if (q0 + px < n) any |= m[px];
+      dead = 0;
+      mbar_init(&qu_full, 1);
+      mbar_init(&do_full, 1);
+      mbar_init(&qc_full, 1);
+      mbar_init(&su_done, 1);
+      mbar_init(&dau_ready, 4);
+      for (int i = 0; i < ST; ++i) {
+        mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
       }
-      if (__any_sync(0xffffffffu, any != 0)) {
+      for (int i = 0; i < NBUF; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&ds_ready[i], 4); }
+      mbar_init(&dqu_full, 1);
+      mbar_init(&dqc_full, 1);
+      mbar_fence_init();
+    }
+    if (lane < kBMaxObj) dcoef_s[lane] = 0.f;
+    __syncwarp();
+    mbar_expect_tx_w(&qu_full, Cfg::QTILE);
+    load_q(sQu, &tm_q, &qu_full, pr);
+    load_k(0, 0);
+    mbar_expect_tx_w(&do_full, 2 * Cfg::QTILE);
+    load_q(sDOu, &tm_do, &do_full, pr);
+    load_q(sDOc, &tm_do, &do_full, pr + B);
+    load_v(0, 0);
+    if (SEPQ) {
+      mbar_expect_tx_w(&qc_full, Cfg::QTILE);
+      load_q(sQc, &tm_q, &qc_full, pr + B);
+    }
+    if (ST >= 2) { load_k(1, 1); load_v(1, 1); }
+    // which objects touch this pixel tile?
+    int cnt = 2;
+    if (lane == 0) { tile_slot[0] = 0; tile_slot[1] = 1; }
+    unsigned int any[kBMaxObj];
+#pragma unroll
+    for (int i = 0; i < kBMaxObj; ++i) {
+      any[i] = 0;
+      if (i < n_obj) {
+        const uint8_t* m = p.mask + ((long long)pr * n_obj + i) * n + q0;
+        if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 3) == 0) && q0 + lane * 4 + 3 < n) {
+          any[i] = *reinterpret_cast<const unsigned int*>(m + lane * 4);
+        } else {
+          for (int j = 0; j < 4; ++j)
+            if (q0 + lane * 4 + j < n) any[i] |= m[lane * 4 + j];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kBMaxObj; ++i) {
+      if (i < n_obj && __any_sync(0xffffffffu, any[i] != 0)) {
         if (lane == 0) tile_slot[cnt] = 2 + i;
         ++cnt;
       }
     }
     if (lane == 0) n_tiles_s = cnt;
+  } else if (warp == 1) {
+    tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
+    tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
@@ -127,132 +177,173 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int T = n_tiles_s;
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
-      mbar_expect_tx_w(&in_full, 3 * Cfg::QTILE);
-      for (int blk = 0; blk < NBLK; ++blk) {
-        tma_load_4d_w(sQ + blk * kBQBlockBytes, &tm_q, &in_full, blk * 64, h, q0, pr);
-        tma_load_4d_w(sDOu + blk * kBQBlockBytes, &tm_do, &in_full, blk * 64, h, q0, pr);
-        tma_load_4d_w(sDOc + blk * kBQBlockBytes, &tm_do, &in_full, blk * 64, h, q0, pr + B);
+    // ===================================== control warp: TMA + MMA issue =====================================
+    constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);
+    constexpr uint64_t mndesc_hi = umma_desc_hi_sw128(kBCBlockBytes, 1024);
+    constexpr uint32_t idesc_s = umma_idesc_f16(128, 80, 0, 0);      // [128 x D] x [80 x D]^T
+    constexpr uint32_t idesc_dq = umma_idesc_f16(128, DMMA, 0, 1);   // dS[128 x 80] x K[80 x D]
+    const uint32_t qu_addr = smem_u32(sQu), qc_addr = smem_u32(sQc), dau_addr = smem_u32(sDOu), doc_addr = smem_u32(sDOc);
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+
+    // D[col] = A[128 x D] (smem, K-major) * Bt[80 x D] (smem, K-major)
+    auto issue_nt = [&](uint32_t col, uint32_t a_addr, uint32_t b_addr) {
+#pragma unroll
+      for (int k = 0; k < DMMA / 16; ++k) {
+        const uint32_t aoff = (k / 4) * kBQBlockBytes + (k % 4) * 32;
+        const uint32_t boff = (k / 4) * kBCBlockBytes + (k % 4) * 32;
+        umma_ss_w(tmem + col, umma_desc(kdesc_hi, a_addr + aoff), umma_desc(kdesc_hi, b_addr + boff), idesc_s, k > 0);
       }
-      bool ok = true;
-      for (int t = 0; t < T && ok; ++t) {
-        const int st = t % ST, slot = pr * n_slots + tile_slot[t];
-        ok = mbar_wait_warp(&kv_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 10);
-        if (!ok) break;
-        mbar_expect_tx_w(&kv_full[st], 2 * Cfg::CTILE);
-        for (int blk = 0; blk < NBLK; ++blk) {
-          tma_load_4d_w(sK + (st * NBLK + blk) * kBCBlockBytes, &tm_k, &kv_full[st], blk * 64, h, 0, slot);
-          tma_load_4d_w(sV + (st * NBLK + blk) * kBCBlockBytes, &tm_v, &kv_full[st], blk * 64, h, 0, slot);
-        }
-        if (t == 0) {
-          // re-fill the Q buffer with the conditional row once S_u = Q_u K_0^T has been computed
-          ok = mbar_wait_warp(&qu_done, 0, &dead, p.err, 12);
-          if (!ok) break;
-          mbar_expect_tx_w(&q2_full, Cfg::QTILE);
-          for (int blk = 0; blk < NBLK; ++blk)
-            tma_load_4d_w(sQ + blk * kBQBlockBytes, &tm_q, &q2_full, blk * 64, h, q0, pr + B);
+    };
+    // dQ_(t ? c : u) (+)= dS_t (TMEM, packed fp16) * K_t [80 x D] (smem, MN-major)
+    auto issue_dq = [&](int t) {
+      const int st = t % ST;
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        umma_ts_w(tmem + Cfg::TMEM_DQ + (t ? DMMA : 0), tmem + (t % NBUF) * 160 + k * 8,
+                  umma_desc(mndesc_hi, k_addr + st * Cfg::CTILE + k * 2048), idesc_dq, (t >= 2) || k > 0);
+      umma_commit_w(&k_empty[st]);
+    };
+
+    int k_next = T < ST ? T : ST, v_next = k_next;
+    for (int t = 2; t < k_next; ++t) { load_k(t, tile_slot[t]); load_v(t, tile_slot[t]); }
+    int sdp_issued = 0, dq_issued = 0;
+    bool ok = true;
+
+    auto issue_sdp = [&](int t) {  // conditional-row task t >= 1
+      const int st = t % ST;
+      ok = mbar_wait_warp(&qc_full, 0, &dead, p.err, 23) &&
+           mbar_wait_warp(&k_full[st], (t / ST) & 1, &dead, p.err, 24) &&
+           mbar_wait_warp(&v_full[st], (t / ST) & 1, &dead, p.err, 25);
+      if (!ok) return;
+      tc_fence_after();
+      issue_nt((t % NBUF) * 160, qc_addr, k_addr + st * Cfg::CTILE);
+      issue_nt((t % NBUF) * 160 + 80, doc_addr, v_addr + st * Cfg::CTILE);
+      umma_commit_w(&sdp_full[t % NBUF]);
+      umma_commit_w(&v_empty[st]);
+    };
+    auto refill = [&]() {
+      while (ok && k_next < T && k_next - ST < dq_issued) {
+        ok = mbar_wait_warp(&k_empty[k_next % ST], (k_next / ST - 1) & 1, &dead, p.err, 10);
+        if (ok) load_k(k_next, tile_slot[k_next]);
+        ++k_next;
+      }
+      while (ok && v_next < T && v_next - ST < sdp_issued) {
+        ok = mbar_wait_warp(&v_empty[v_next % ST], (v_next / ST - 1) & 1, &dead, p.err, 11);
+        if (ok) load_v(v_next, tile_slot[v_next]);
+        ++v_next;
+      }
+    };
+
+    // ---- task 0: S_u = Q_u K_0^T now, dP_u = dA_u V_0^T once warpgroup 0 has formed dA_u ----
+    ok = mbar_wait_warp(&qu_full, 0, &dead, p.err, 20) && mbar_wait_warp(&k_full[0], 0, &dead, p.err, 21);
+    if (ok) {
+      tc_fence_after();
+      issue_nt(0, qu_addr, k_addr);
+      if (!SEPQ) {
+        umma_commit_w(&su_done);
+        ok = mbar_wait_warp(&su_done, 0, &dead, p.err, 12);
+        if (ok) {
+          mbar_expect_tx_w(&qc_full, Cfg::QTILE);
+          load_q(sQc, &tm_q, &qc_full, pr + B);
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
-      constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);
-      constexpr uint64_t mndesc_hi = umma_desc_hi_sw128(kBCBlockBytes, 1024);
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 80, 0, 0);      // [128 x D] x [80 x D]^T
-      constexpr uint32_t idesc_dq = umma_idesc_f16(128, DMMA, 0, 1);   // dS[128 x 80] x K[80 x D]
-      const uint32_t q_addr = smem_u32(sQ), dou_addr = smem_u32(sDOu), doc_addr = smem_u32(sDOc);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    if (ok) ok = mbar_wait_warp(&dau_ready, 0, &dead, p.err, 22) && mbar_wait_warp(&v_full[0], 0, &dead, p.err, 26);
+    if (ok) {
+      tc_fence_after();
+      issue_nt(80, dau_addr, v_addr);
+      umma_commit_w(&sdp_full[0]);
+      umma_commit_w(&v_empty[0]);
+      sdp_issued = 1;
+    }
+    while (ok && sdp_issued < T && sdp_issued < NBUF) { refill(); if (ok) issue_sdp(sdp_issued); ++sdp_issued; }
 
-      // D[slot] = A[128 x D] (smem, K-major) * Bt[80 x D] (smem, K-major)
-      auto issue_nt = [&](int slot, uint32_t a_addr, uint32_t b_addr) {
-#pragma unroll
-        for (int k = 0; k < DMMA / 16; ++k) {
-          const uint32_t aoff = (k / 4) * kBQBlockBytes + (k % 4) * 32;
-          const uint32_t boff = (k / 4) * kBCBlockBytes + (k % 4) * 32;
-          umma_ss_w(tmem + slot * 80, umma_desc(kdesc_hi, a_addr + aoff), umma_desc(kdesc_hi, b_addr + boff), idesc_s,
-                  k > 0);
-        }
-      };
-      // dQ (+)= dS[slot] (TMEM, packed fp16) * K[80 x D] (smem, MN-major)
-      auto issue_dq = [&](int slot, uint32_t kk_addr, bool acc) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-          umma_ts_w(tmem + Cfg::TMEM_DQ, tmem + slot * 80 + k * 8, umma_desc(mndesc_hi, kk_addr + k * 2048), idesc_dq,
-                  acc || k > 0);
-      };
-      auto issue_sdp = [&](int t) {  // conditional-row tile t >= 1 into pair (t & 1)
-        const int st = t % ST, s_slot = (t & 1) * 2;
-        issue_nt(s_slot, q_addr, k_addr + st * Cfg::CTILE);
-        issue_nt(s_slot + 1, doc_addr, v_addr + st * Cfg::CTILE);
-        umma_commit_w(&sdp_full[t & 1]);
-      };
-
-      bool ok = mbar_wait_warp(&in_full, 0, &dead, p.err, 20) && mbar_wait_warp(&kv_full[0], 0, &dead, p.err, 21);
-      if (ok) {
-        tc_fence_after();
-        issue_nt(0, q_addr, k_addr);
-        umma_commit_w(&qu_done);
-        issue_nt(1, dou_addr, v_addr);
-        issue_nt(2, doc_addr, v_addr);
-        umma_commit_w(&sdp_full[0]);
-        ok = mbar_wait_warp(&ds_ready, 0, &dead, p.err, 22);
-      }
-      if (ok) {
-        tc_fence_after();
-        issue_dq(0, k_addr, false);
-        umma_commit_w(&dq_full);
-        umma_commit_w(&kv_empty[0]);
-        ok = mbar_wait_warp(&q2_full, 0, &dead, p.err, 23) && mbar_wait_warp(&kv_full[1 % ST], (1 / ST) & 1, &dead, p.err, 24);
-      }
-      if (ok) {
-        tc_fence_after();
-        issue_sdp(1);
-      }
-      for (int t = 1; t < T && ok; ++t) {
-        const int st = t % ST;
-        if (Cfg::PREFETCH && t + 1 < T) {
-          ok = mbar_wait_warp(&kv_full[(t + 1) % ST], ((t + 1) / ST) & 1, &dead, p.err, 25);
-          if (!ok) break;
-          tc_fence_after();
-          issue_sdp(t + 1);
-        }
-        ok = mbar_wait_warp(&ds_ready, t & 1, &dead, p.err, 26);
-        if (ok && t == 1) ok = mbar_wait_warp(&dq_drained, 0, &dead, p.err, 27);
-        if (!ok) break;
-        tc_fence_after();
-        issue_dq((t & 1) * 2, k_addr + st * Cfg::CTILE, t > 1);
-        if (t == T - 1) umma_commit_w(&dq_full);
-        umma_commit_w(&kv_empty[st]);
-        if (!Cfg::PREFETCH && t + 1 < T) {
-          ok = mbar_wait_warp(&kv_full[(t + 1) % ST], ((t + 1) / ST) & 1, &dead, p.err, 28);
-          if (!ok) break;
-          tc_fence_after();
-          issue_sdp(t + 1);
-        }
-      }
+    for (int t = 0; t < T && ok; ++t) {
+      refill();
+      if (!ok) break;
+      ok = mbar_wait_warp(&ds_ready[t % NBUF], (t / NBUF) & 1, &dead, p.err, 27);
+      if (!ok) break;
+      tc_fence_after();
+      issue_dq(t);
+      dq_issued = t + 1;
+      if (t == 0) umma_commit_w(&dqu_full);
+      if (t == T - 1) umma_commit_w(&dqc_full);
+      // next [S | dP] pair into the buffer this dQ just consumed (in-order tensor pipe: safe behind issue_dq)
+      if (sdp_issued < T && k_next > sdp_issued && v_next > sdp_issued) { issue_sdp(sdp_issued); ++sdp_issued; }
+      refill();
+      if (ok && sdp_issued < T && sdp_issued <= t + NBUF) { issue_sdp(sdp_issued); ++sdp_issued; }
     }
   } else {
     // ===================================== per-row math ======================================
-    const int row = q0 + ((warp & 3) << 5) + lane;
+    const int g = (warp - 1) >> 2;  // math warpgroup
+    const int quad = warp & 3;      // TMEM lane quadrant this warp may access
+    const int r = (quad << 5) + lane;
+    const int row = q0 + r;
     const bool row_ok = row < n;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad << 5) << 16);
     const float kLog2e = 1.4426950408889634f;
     const float* lse_row = p.lse + ((long long)pr * p.heads + h) * n_slots * n + row;
 
+    unsigned int bits = 0;
     float sigma = 0.f;
-    for (int i = 0; i < n_obj; ++i) {
-      const float mk = row_ok ? (float)p.mask[((long long)pr * n_obj + i) * n + row] : 0.f;
-      sigma += mk * p.coef[pr * n_obj + i];
+#pragma unroll
+    for (int i = 0; i < kBMaxObj; ++i) {
+      if (i < n_obj) {
+        const bool mk = row_ok && p.mask[((long long)pr * n_obj + i) * n + row] != 0;
+        if (mk) { bits |= 1u << i; sigma += p.coef[pr * n_obj + i]; }
+      }
     }
 
-    auto write_dq = [&](int batch_row) {
+    bool ok = true;
+    float delta_uc = 0.f;
+    if (n_obj > 0 || g == 0) ok = mbar_wait_warp(&do_full, 0, &dead, p.err, 29);
+    if (ok && n_obj > 0) {
+      // delta_uc = <dO_c[row], out_u[row]> over this head's D channels (dO_c from the staged tile, out_u from global)
+      const __half* orow = p.out + (long long)pr * p.o_batch_stride + (long long)row * p.o_token_stride + h * D;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) {
+        const uint4 dv = *reinterpret_cast<const uint4*>(sDOc + (c / 8) * kBQBlockBytes + sw128_offset(r, c % 8));
+        uint4 ov = make_uint4(0, 0, 0, 0);
+        if (row_ok) ov = *reinterpret_cast<const uint4*>(orow + c * 8);
+        const __half2* dh = reinterpret_cast<const __half2*>(&dv);
+        const __half2* oh = reinterpret_cast<const __half2*>(&ov);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __half22float2(dh[i]), b = __half22float2(oh[i]);
+          delta_uc = fmaf(a.x, b.x, delta_uc);
+          delta_uc = fmaf(a.y, b.y, delta_uc);
+        }
+      }
+    }
+    if (g == 0) {
+      // dA_u = dO_u - sigma dO_c, in place over the dO_u tile (skipped by warps whose pixels touch no object)
+      if (ok && __any_sync(0xffffffffu, sigma != 0.f)) {
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+          const uint32_t off = (c / 8) * kBQBlockBytes + sw128_offset(r, c % 8);
+          uint4 uv = *reinterpret_cast<const uint4*>(sDOu + off);
+          const uint4 cv = *reinterpret_cast<const uint4*>(sDOc + off);
+          __half2* uh = reinterpret_cast<__half2*>(&uv);
+          const __half2* ch = reinterpret_cast<const __half2*>(&cv);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 a = __half22float2(uh[i]), b = __half22float2(ch[i]);
+            uh[i] = __floats2half2_rn(fmaf(-sigma, b.x, a.x), fmaf(-sigma, b.y, a.y));
+          }
+          *reinterpret_cast<uint4*>(sDOu + off) = uv;
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dau_ready);
+    }
+
+    auto write_dq = [&](int batch_row, uint32_t col) {
       __half* drow = p.d_q + ((long long)batch_row * n + row) * (p.heads * D) + h * D;
 #pragma unroll
       for (int c0 = 0; c0 < D; c0 += 8) {
         uint32_t o[8];
-        tmem_ld8(lane_addr + Cfg::TMEM_DQ + c0, o);
+        tmem_ld8(lane_addr + col + c0, o);
         tmem_ld_wait();
         if (row_ok) {
           uint4 v;
@@ -265,123 +356,98 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
     };
 
-    // ---------------- tile 0: unconditional row ----------------
-    float delta_uc = 0.f;
-    bool ok = mbar_wait_warp(&sdp_full[0], 0, &dead, p.err, 30);
-    if (ok) {
-      tc_fence_after();
-      const float lse2 = row_ok ? lse_row[0] * kLog2e : 0.f;
-      float du = 0.f, duc = 0.f;
-#pragma unroll
-      for (int c0 = 0; c0 < 80; c0 += 16) {
-        uint32_t s[16], a[16], c[16];
-        tmem_ld16(lane_addr + c0, s);
-        tmem_ld16(lane_addr + 80 + c0, a);
-        tmem_ld16(lane_addr + 160 + c0, c);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float pp = (c0 + i < p.ctx_len) ? fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lse2)) : 0.f;
-          const float dpc = __uint_as_float(c[i]);
-          du = fmaf(pp, fmaf(-sigma, dpc, __uint_as_float(a[i])), du);
-          duc = fmaf(pp, dpc, duc);
-        }
-      }
-      delta_uc = duc;
-#pragma unroll
-      for (int c0 = 0; c0 < 80; c0 += 16) {
-        uint32_t s[16], a[16], c[16], pk[8];
-        tmem_ld16(lane_addr + c0, s);
-        tmem_ld16(lane_addr + 80 + c0, a);
-        tmem_ld16(lane_addr + 160 + c0, c);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float pp = (c0 + i < p.ctx_len) ? fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lse2)) : 0.f;
-          const float dp = fmaf(-sigma, __uint_as_float(c[i]), __uint_as_float(a[i]));
-          s[i] = __float_as_uint(p.scale * pp * (dp - du));
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_half2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
-        tmem_st8(lane_addr + (c0 >> 1), pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ds_ready);
-      ok = mbar_wait_warp(&dq_full, 0, &dead, p.err, 31);
-    }
-    if (ok) {
-      tc_fence_after();
-      write_dq(pr);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dq_drained);
-    }
-    // ---------------- tiles 1..T-1: conditional row ----------------
-    for (int t = 1; t < T && ok; ++t) {
+    for (int t = g; t < T && ok; t += NBUF) {
       const int slot = tile_slot[t];
-      const uint32_t s_addr = lane_addr + (t & 1) * 160;
-      float w = 1.f, mk = 0.f;
+      const uint32_t s_addr = lane_addr + (t % NBUF) * 160;
+      float w = 1.f;
+      bool mk = false, live = true;
       if (slot >= 2) {
-        mk = row_ok ? (float)p.mask[((long long)pr * n_obj + (slot - 2)) * n + row] : 0.f;
-        w = mk * p.coef[pr * n_obj + (slot - 2)];
+        mk = (bits >> (slot - 2)) & 1u;
+        w = mk ? p.coef[pr * n_obj + slot - 2] : 0.f;
+        live = __any_sync(0xffffffffu, mk);
       }
-      const float lse2 = row_ok ? lse_row[(long long)slot * n] * kLog2e : 0.f;
-      ok = mbar_wait_warp(&sdp_full[t & 1], (t >> 1) & 1, &dead, p.err, 32);
+      const float lse2 = (live && row_ok) ? lse_row[(long long)slot * n] * kLog2e : 0.f;
+      ok = mbar_wait_warp(&sdp_full[t % NBUF], (t / NBUF) & 1, &dead, p.err, 32);
       if (!ok) break;
       tc_fence_after();
       float delta = 0.f;
-#pragma unroll
-      for (int c0 = 0; c0 < 80; c0 += 16) {
-        uint32_t s[16], a[16];
-        tmem_ld16(s_addr + c0, s);
-        tmem_ld16(s_addr + 80 + c0, a);
+      if (live) {
+        uint32_t s[80];
+        tmem_ld32(s_addr, s);
+        tmem_ld32(s_addr + 32, s + 32);
+        tmem_ld16(s_addr + 64, s + 64);
         tmem_ld_wait();
+        const int valid = p.ctx_len;
+        if (valid >= 76) {  // CLIP's 77 tokens: only the last columns are padding (exp2(-inf) = 0)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float pp = (c0 + i < p.ctx_len) ? fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lse2)) : 0.f;
-          delta = fmaf(pp, __uint_as_float(a[i]), delta);
-        }
-      }
-      const float ws = w * p.scale;
+          for (int c = 76; c < 80; ++c)
+            if (c >= valid) s[c] = 0xff800000u;
+        } else {
 #pragma unroll
-      for (int c0 = 0; c0 < 80; c0 += 16) {
-        uint32_t s[16], a[16], pk[8];
-        tmem_ld16(s_addr + c0, s);
-        tmem_ld16(s_addr + 80 + c0, a);
-        tmem_ld_wait();
+          for (int c = 0; c < 76; ++c)
+            if (c >= valid) s[c] = 0xff800000u;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float pp = (c0 + i < p.ctx_len) ? fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lse2)) : 0.f;
-          s[i] = __float_as_uint(ws * pp * (__uint_as_float(a[i]) - delta));
+          for (int c = 76; c < 80; ++c) s[c] = 0xff800000u;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_half2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
-        tmem_st8(s_addr + (c0 >> 1), pk);
+        for (int c = 0; c < 80; ++c)
+          s[c] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2, -lse2)));
+#pragma unroll
+        for (int c0 = 0; c0 < 80; c0 += 16) {
+          uint32_t a[16];
+          tmem_ld16(s_addr + 80 + c0, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) delta = fmaf(__uint_as_float(s[c0 + i]), __uint_as_float(a[i]), delta);
+        }
+        const float ws = w * p.scale;
+#pragma unroll
+        for (int c0 = 0; c0 < 80; c0 += 16) {
+          uint32_t a[16], pk[8];
+          tmem_ld16(s_addr + 80 + c0, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pk[i] = pack_half2(ws * __uint_as_float(s[c0 + 2 * i]) * (__uint_as_float(a[2 * i]) - delta),
+                               ws * __uint_as_float(s[c0 + 2 * i + 1]) * (__uint_as_float(a[2 * i + 1]) - delta));
+          tmem_st8(s_addr + (c0 >> 1), pk);
+        }
+      } else {
+        uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int c0 = 0; c0 < 40; c0 += 8) tmem_st8(s_addr + c0, z);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ds_ready);
-      if (slot >= 2) {
-        float val = mk * (delta - delta_uc);
+      if (lane == 0) mbar_arrive(&ds_ready[t % NBUF]);
+      if (slot >= 2 && live) {
+        float val = mk ? (delta - delta_uc) : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
         if (lane == 0) atomicAdd(&dcoef_s[slot - 2], val);
       }
+      if (t == 0) {  // dQ_u is complete as soon as the (single) unconditional task's dS has been consumed
+        ok = mbar_wait_warp(&dqu_full, 0, &dead, p.err, 31);
+        if (ok) {
+          tc_fence_after();
+          write_dq(pr, Cfg::TMEM_DQ);
+        }
+      }
     }
     ok = __all_sync(0xffffffffu, ok);
-    if (ok) ok = mbar_wait_warp(&dq_full, 1, &dead, p.err, 33);
-    if (ok) {
-      tc_fence_after();
-      write_dq(pr + B);
+    if (g == NBUF - 1) {  // the warpgroup that owns task 1 stores the conditional row
+      if (ok) ok = mbar_wait_warp(&dqc_full, 0, &dead, p.err, 33);
+      if (ok) {
+        tc_fence_after();
+        write_dq(pr + B, Cfg::TMEM_DQ + DMMA);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (tid < n_obj && dcoef_s[tid] != 0.f) atomicAdd(&p.d_coef[pr * n_obj + tid], dcoef_s[tid]);
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
 }
 
 template <int D>
@@ -413,6 +479,7 @@ static int launch_xattn_bwd(const sta_xattn_bwd_args* a, cudaStream_t stream) {
   p.mask = a->mask;
   p.coef = a->coef;
   p.lse = a->lse;
+  p.out = reinterpret_cast<const __half*>(a->out);
   p.d_q = reinterpret_cast<__half*>(a->d_q);
   p.d_coef = a->d_coef;
   p.prompts = a->prompts;
@@ -420,14 +487,16 @@ static int launch_xattn_bwd(const sta_xattn_bwd_args* a, cudaStream_t stream) {
   p.heads = a->heads;
   p.n_obj = a->n_obj;
   p.ctx_len = a->ctx_len;
+  p.o_token_stride = a->o_token_stride;
+  p.o_batch_stride = a->o_batch_stride;
   p.scale = a->scale;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.err = device_error_word();
-  static bool attr_set = false;
-  if (!attr_set) {
-    STA_CUDA_CHECK(cudaFuncSetAttribute(xattn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce smem_attr;
+  int rc = smem_attr.run([] {
+    return cudaFuncSetAttribute(xattn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  if (rc) return rc;
   if (a->n_obj > 0)
     STA_CUDA_CHECK(cudaMemsetAsync(a->d_coef, 0, sizeof(float) * a->prompts * a->n_obj, stream));
   dim3 grid((a->n + 127) / 128, a->heads, a->prompts);
@@ -444,9 +513,12 @@ extern "C" int sta_xattn_bwd(const sta_xattn_bwd_args* a, void* stream) {
     return fail(STA_ERR_BAD_ARG, "sta_xattn_bwd: null pointer");
   if (a->prompts < 1 || a->n < 1 || a->heads < 1) return fail(STA_ERR_BAD_ARG, "sta_xattn_bwd: empty shape");
   if (a->n_obj < 0 || a->n_obj > kBMaxObj) return fail(STA_ERR_UNSUPPORTED, "sta_xattn_bwd: n_obj %d not in [0,%d]", a->n_obj, kBMaxObj);
-  if (a->n_obj > 0 && (!a->mask || !a->coef || !a->d_coef)) return fail(STA_ERR_BAD_ARG, "sta_xattn_bwd: mask/coef/d_coef required when n_obj > 0");
+  if (a->n_obj > 0 && (!a->mask || !a->coef || !a->d_coef || !a->out))
+    return fail(STA_ERR_BAD_ARG, "sta_xattn_bwd: mask/coef/d_coef/out required when n_obj > 0");
   if (a->ctx_len < 1 || a->ctx_len > 80) return fail(STA_ERR_UNSUPPORTED, "sta_xattn_bwd: ctx_len %d not in [1,80]", a->ctx_len);
   if (reinterpret_cast<uintptr_t>(a->d_q) & 15) return fail(STA_ERR_UNSUPPORTED, "sta_xattn_bwd: d_q must be 16-byte aligned");
+  if (a->n_obj > 0 && ((a->o_token_stride % 8) || (a->o_batch_stride % 8) || (reinterpret_cast<uintptr_t>(a->out) & 15)))
+    return fail(STA_ERR_UNSUPPORTED, "sta_xattn_bwd: out rows must be 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (a->head_dim) {
     case 40: return launch_xattn_bwd<40>(a, s);

@@ -9,13 +9,26 @@
 // the conditional row accumulates into ONE TMEM accumulator; the unconditional accumulator is subtracted with
 // weight sum_i w_i in the fp32 epilogue.
 //
-// CTA = one 128-pixel tile of one (prompt, head); 10 warps:
-//   warp 0      TMA producer: Q_u and Q_c tiles, then the K/V tiles (80 rows, rows 77..79 zero-filled by TMA)
-//               of every ACTIVE context (an object whose mask is empty inside this pixel tile is skipped)
-//   warp 1      MMA issuer: S = Q K^T (SS), O += P V (TS, P packed fp16 in TMEM, V MN-major)
-//   warps 2..5  softmax + epilogue of the unconditional row (one context)
-//   warps 6..9  softmax + epilogue of the conditional row (1 + active objects contexts)
-// TMEM columns: S_u [0,96) S_c [96,192) (P aliases S), O_u at 192, O_c at 192 + DMMA.
+// The op is microseconds of work per launch (1.6 GFLOP / 11 MB at the 64x64 level): it is bound by the latency
+// chain TMA -> MMA -> softmax -> MMA -> store and by the MUFU pipe (one ex2 per score), not by the tensor pipe.
+// Round-2 layout, built for that:
+//   CTA = one 128-pixel tile of one (prompt, head); 9 warps:
+//     warp 0      control: barrier init, ALL TMA loads (issued before anything else: Q_u, K_0, Q_c, K_1, V_0, V_1,
+//                 then the live objects), MMA issue (S = Q K^T SS, O += P V TS with P packed fp16 in TMEM and V
+//                 MN-major), ring refills
+//     warps 1..4  softmax warpgroup 0: contexts ("tasks") 0, 2, 4, ...  + the unconditional row's epilogue
+//     warps 5..8  softmax warpgroup 1: tasks 1, 3, 5, ...               + the conditional row's epilogue
+//   task 0 = (Q_u, unconditional context), task 1 = (Q_c, global context), tasks 2.. = (Q_c, local context of an
+//   object whose mask is non-empty inside this pixel tile).  Task t uses S buffer t & 1: the two warpgroups run their
+//   softmaxes concurrently and QK^T of task t + 2 is issued right behind P V of task t (tcgen05.mma executes in
+//   issue order, so the S buffer that P_t aliases is safe).
+//   TMEM: S0 [0,80) S1 [80,160) (P aliases the first 40 columns of its S), O_u at 160, O_c at 160 + DMMA: 256
+//   columns at head dim 40, so TWO CTAs are resident per SM there (288 threads, <= 112 registers, 93 KB smem) and
+//   the 256 CTAs of the 64x64 level run as a single wave.
+//   A warp whose 32 pixels are all outside object i's mask skips that softmax (P = 0); LSE is written only for
+//   the (context, pixel) pairs that were evaluated (the backward applies the same rule).
+#include <mutex>
+
 #include "../../include/sta_b200.h"
 #include "sta_common.cuh"
 #include "sta_host.h"
@@ -30,16 +43,34 @@ template <int D>
 struct XattnCfg {
   static constexpr int DMMA = (D + 15) / 16 * 16;
   static constexpr int NBLK = (D + 63) / 64;
-  static constexpr int ST = (NBLK == 3) ? 2 : 3;  // K and V ring depth
+  static constexpr int ST = (NBLK == 1) ? 3 : (NBLK == 2 ? 4 : 2);  // K and V ring depth
   static constexpr int QTILE = NBLK * kXQBlockBytes;
   static constexpr int CTILE = NBLK * kXCBlockBytes;
   static constexpr int SMEM_BYTES = 2 * QTILE + 2 * ST * CTILE + 1024;
-  static constexpr int THREADS = 320;
-  static constexpr int TMEM_S = 96;
-  static constexpr int TMEM_O = 192;
+  static constexpr int THREADS = 288;
+  static constexpr int TMEM_O = 160;
+  static constexpr int TMEM_COLS = (TMEM_O + 2 * DMMA <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (TMEM_COLS == 256) ? 2 : 1;
 };
 
+// Debug-only CTA timeline (tools/xattn_timeline.py builds a separate library with -DSTA_TIMELINE; never in the product).
+#ifdef STA_TIMELINE
+static long long* g_timeline_fwd = nullptr;
+#define STA_TL(i)                                                                                     \
+  do {                                                                                                \
+    if (p.tl && lane == 0)                                                                            \
+      p.tl[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = clock64(); \
+  } while (0)
+#else
+#define STA_TL(i) \
+  do {            \
+  } while (0)
+#endif
+
 struct XattnFwdParams {
+#ifdef STA_TIMELINE
+  long long* tl;
+#endif
   const uint8_t* mask;  // [B, n_obj, n]
   const float* coef;    // [B, n_obj]
   __half* out;
@@ -51,7 +82,7 @@ struct XattnFwdParams {
 };
 
 template <int D>
-__global__ void __launch_bounds__(XattnCfg<D>::THREADS, 1)
+__global__ void __launch_bounds__(XattnCfg<D>::THREADS, XattnCfg<D>::MIN_CTAS)
 xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const XattnFwdParams p) {
   using Cfg = XattnCfg<D>;
@@ -60,229 +91,289 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem =
       reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sQ = smem;
+  unsigned char* sQ = smem;  // Q_u tile, Q_c tile
   unsigned char* sK = sQ + 2 * Cfg::QTILE;
   unsigned char* sV = sK + ST * Cfg::CTILE;
 
-  __shared__ uint64_t q_full, k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
-  __shared__ uint64_t s_full[2], p_ready[2], o_full[2];
+  __shared__ uint64_t qu_full, qc_full, k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
+  __shared__ uint64_t s_full[2], p_ready[2], ou_full, o_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
-  __shared__ int tile_slot[2 + kXMaxObj];  // context slot of the t-th tile this CTA processes
+  __shared__ int tile_slot[2 + kXMaxObj];  // context slot of the t-th task of this CTA
   __shared__ int n_tiles_s;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, pr = blockIdx.z;
   const int n = p.n, B = p.prompts, n_obj = p.n_obj, n_slots = 2 + p.n_obj;
+  if (warp == 0) STA_TL(0);
 
-  if (tid == 0) {
-    dead = 0;
-    mbar_init(&q_full, 1);
-    for (int i = 0; i < ST; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(&tmem_base_s, 512);
-    tmem_relinquish();
-  }
+  auto load_k = [&](int t, int slot) {
+    const int st = t % ST;
+    mbar_expect_tx_w(&k_full[st], Cfg::CTILE);
+    for (int blk = 0; blk < NBLK; ++blk)
+      tma_load_4d_w(sK + (st * NBLK + blk) * kXCBlockBytes, &tm_k, &k_full[st], blk * 64, h, 0, pr * n_slots + slot);
+  };
+  auto load_v = [&](int t, int slot) {
+    const int st = t % ST;
+    mbar_expect_tx_w(&v_full[st], Cfg::CTILE);
+    for (int blk = 0; blk < NBLK; ++blk)
+      tma_load_4d_w(sV + (st * NBLK + blk) * kXCBlockBytes, &tm_v, &v_full[st], blk * 64, h, 0, pr * n_slots + slot);
+  };
+
   if (warp == 0) {
-    // which objects touch this pixel tile?  (128 mask bytes per object: one 4-byte word per lane)
     if (lane == 0) {
-      tma_prefetch_desc(&tm_q);
-      tma_prefetch_desc(&tm_k);
-      tma_prefetch_desc(&tm_v);
+      dead = 0;
+      mbar_init(&qu_full, 1);
+      mbar_init(&qc_full, 1);
+      for (int i = 0; i < ST; ++i) {
+        mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+        mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
+      mbar_init(&ou_full, 1);
+      mbar_init(&o_full, 1);
+      mbar_fence_init();
     }
+    __syncwarp();
+    // every load that does not depend on the masks goes out before anything else happens in this CTA
+    mbar_expect_tx_w(&qu_full, Cfg::QTILE);
+    for (int blk = 0; blk < NBLK; ++blk) tma_load_4d_w(sQ + blk * kXQBlockBytes, &tm_q, &qu_full, blk * 64, h, q0, pr);
+    load_k(0, 0);
+    mbar_expect_tx_w(&qc_full, Cfg::QTILE);
+    for (int blk = 0; blk < NBLK; ++blk)
+      tma_load_4d_w(sQ + (NBLK + blk) * kXQBlockBytes, &tm_q, &qc_full, blk * 64, h, q0, pr + B);
+    load_k(1, 1);
+    load_v(0, 0);
+    load_v(1, 1);
+    STA_TL(1);
+    // which objects touch this pixel tile?  (128 mask bytes per object: one 4-byte word per lane)
     int cnt = 2;
     if (lane == 0) { tile_slot[0] = 0; tile_slot[1] = 1; }
-    for (int i = 0; i < n_obj; ++i) {
-      const uint8_t* m = p.mask + ((long long)pr * n_obj + i) * n + q0;
-      int any = 0;
+    unsigned int any[kXMaxObj];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int px = lane * 4 + j;
-        if (q0 + px < n) any |= m[px];
+    for (int i = 0; i < kXMaxObj; ++i) {
+      any[i] = 0;
+      if (i < n_obj) {
+        const uint8_t* m = p.mask + ((long long)pr * n_obj + i) * n + q0;
+        if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 3) == 0) && q0 + lane * 4 + 3 < n) {
+          any[i] = *reinterpret_cast<const unsigned int*>(m + lane * 4);
+        } else {
+          for (int j = 0; j < 4; ++j)
+            if (q0 + lane * 4 + j < n) any[i] |= m[lane * 4 + j];
+        }
       }
-      if (__any_sync(0xffffffffu, any != 0)) {
+    }
+#pragma unroll
+    for (int i = 0; i < kXMaxObj; ++i) {
+      if (i < n_obj && __any_sync(0xffffffffu, any[i] != 0)) {
         if (lane == 0) tile_slot[cnt] = 2 + i;
         ++cnt;
       }
     }
     if (lane == 0) n_tiles_s = cnt;
+  } else if (warp == 1) {
+    tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
+    tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const int T = n_tiles_s;  // tile 0 -> unconditional row, tiles 1..T-1 -> conditional row
+  const int T = n_tiles_s;  // task 0 -> unconditional row, tasks 1..T-1 -> conditional row
+  if (warp == 0) STA_TL(2);
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
-      mbar_expect_tx_w(&q_full, 2 * Cfg::QTILE);
-      for (int r = 0; r < 2; ++r)
-        for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d_w(sQ + (r * NBLK + blk) * kXQBlockBytes, &tm_q, &q_full, blk * 64, h, q0, pr + r * B);
-      for (int t = 0; t < T; ++t) {
-        const int st = t % ST, slot = pr * n_slots + tile_slot[t];
-        if (!mbar_wait_warp(&k_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 10)) break;
-        mbar_expect_tx_w(&k_full[st], Cfg::CTILE);
-        for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d_w(sK + (st * NBLK + blk) * kXCBlockBytes, &tm_k, &k_full[st], blk * 64, h, 0, slot);
-        if (!mbar_wait_warp(&v_empty[st], ((t / ST) & 1) ^ 1, &dead, p.err, 11)) break;
-        mbar_expect_tx_w(&v_full[st], Cfg::CTILE);
-        for (int blk = 0; blk < NBLK; ++blk)
-          tma_load_4d_w(sV + (st * NBLK + blk) * kXCBlockBytes, &tm_v, &v_full[st], blk * 64, h, 0, slot);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    {  // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
-      constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);
-      constexpr uint64_t vdesc_hi = umma_desc_hi_sw128(kXCBlockBytes, 1024);
-      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 80, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(128, DMMA, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    // ===================================== control warp: TMA + MMA issue =====================================
+    // whole warp, warp-uniform control flow; single-lane instructions are elected inside the *_w helpers
+    constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);
+    constexpr uint64_t vdesc_hi = umma_desc_hi_sw128(kXCBlockBytes, 1024);
+    constexpr uint32_t idesc_qk = umma_idesc_f16(128, 80, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(128, DMMA, 0, 1);
+    const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
 
-      auto issue_qk = [&](int r, int st) {
+    auto issue_qk = [&](int t) {  // S[t & 1] = Q_(t ? c : u) K_t^T
+      const int st = t % ST, r = t ? 1 : 0;
 #pragma unroll
-        for (int k = 0; k < DMMA / 16; ++k) {
-          const uint32_t qoff = (k / 4) * kXQBlockBytes + (k % 4) * 32;
-          const uint32_t koff = (k / 4) * kXCBlockBytes + (k % 4) * 32;
-          umma_ss_w(tmem + r * Cfg::TMEM_S, umma_desc(kdesc_hi, q_addr + r * Cfg::QTILE + qoff),
+      for (int k = 0; k < DMMA / 16; ++k) {
+        const uint32_t qoff = (k / 4) * kXQBlockBytes + (k % 4) * 32;
+        const uint32_t koff = (k / 4) * kXCBlockBytes + (k % 4) * 32;
+        umma_ss_w(tmem + (t & 1) * 80, umma_desc(kdesc_hi, q_addr + r * Cfg::QTILE + qoff),
                   umma_desc(kdesc_hi, k_addr + st * Cfg::CTILE + koff), idesc_qk, k > 0);
-        }
-        umma_commit_w(&s_full[r]);
-        umma_commit_w(&k_empty[st]);
-      };
-      auto issue_pv = [&](int r, int st, bool acc) {
+      }
+      umma_commit_w(&s_full[t & 1]);
+      umma_commit_w(&k_empty[st]);
+    };
+    auto issue_pv = [&](int t) {  // O_(t ? c : u) (+)= P_t V_t
+      const int st = t % ST, r = t ? 1 : 0;
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
-          umma_ts_w(tmem + Cfg::TMEM_O + r * DMMA, tmem + r * Cfg::TMEM_S + k * 8,
-                  umma_desc(vdesc_hi, v_addr + st * Cfg::CTILE + k * 2048), idesc_pv, acc || k > 0);
-        umma_commit_w(&v_empty[st]);
-      };
+      for (int k = 0; k < 5; ++k)
+        umma_ts_w(tmem + Cfg::TMEM_O + r * DMMA, tmem + (t & 1) * 80 + k * 8,
+                  umma_desc(vdesc_hi, v_addr + st * Cfg::CTILE + k * 2048), idesc_pv, (t >= 2) || k > 0);
+      umma_commit_w(&v_empty[st]);
+    };
 
-      bool ok = mbar_wait_warp(&q_full, 0, &dead, p.err, 20) && mbar_wait_warp(&k_full[0], 0, &dead, p.err, 21);
-      if (ok) {
-        tc_fence_after();
-        issue_qk(0, 0);
-        ok = mbar_wait_warp(&k_full[1 % ST], (1 / ST) & 1, &dead, p.err, 22);
+    int k_next = T < ST ? T : ST, v_next = k_next;
+    for (int t = 2; t < k_next; ++t) { load_k(t, tile_slot[t]); load_v(t, tile_slot[t]); }
+
+    bool ok = mbar_wait_warp(&qu_full, 0, &dead, p.err, 20) && mbar_wait_warp(&k_full[0], 0, &dead, p.err, 21);
+    STA_TL(3);
+    if (ok) {
+      tc_fence_after();
+      issue_qk(0);
+      ok = mbar_wait_warp(&qc_full, 0, &dead, p.err, 22) && mbar_wait_warp(&k_full[1], 0, &dead, p.err, 23);
+    }
+    if (ok) {
+      tc_fence_after();
+      issue_qk(1);
+    }
+    for (int t = 0; t < T && ok; ++t) {
+      // ring refills whose predecessor MMA was issued at least one iteration ago (their completion is imminent)
+      while (ok && k_next < T && k_next - ST <= t + 1) {
+        ok = mbar_wait_warp(&k_empty[k_next % ST], (k_next / ST - 1) & 1, &dead, p.err, 10);
+        if (ok) load_k(k_next, tile_slot[k_next]);
+        ++k_next;
       }
-      if (ok) {
-        tc_fence_after();
-        issue_qk(1, 1 % ST);
-        ok = mbar_wait_warp(&p_ready[0], 0, &dead, p.err, 23) && mbar_wait_warp(&v_full[0], 0, &dead, p.err, 24);
+      while (ok && v_next < T && v_next - ST <= t - 1) {
+        ok = mbar_wait_warp(&v_empty[v_next % ST], (v_next / ST - 1) & 1, &dead, p.err, 11);
+        if (ok) load_v(v_next, tile_slot[v_next]);
+        ++v_next;
       }
-      if (ok) {
-        tc_fence_after();
-        issue_pv(0, 0, false);
-        umma_commit_w(&o_full[0]);
-      }
-      for (int t = 1; t < T && ok; ++t) {
-        const int st = t % ST;
-        ok = mbar_wait_warp(&p_ready[1], (t - 1) & 1, &dead, p.err, 25) &&
-             mbar_wait_warp(&v_full[st], (t / ST) & 1, &dead, p.err, 26);
+      if (!ok) break;
+      ok = mbar_wait_warp(&p_ready[t & 1], (t >> 1) & 1, &dead, p.err, 24) &&
+           mbar_wait_warp(&v_full[t % ST], (t / ST) & 1, &dead, p.err, 25);
+      if (!ok) break;
+      tc_fence_after();
+      if (t == 0) STA_TL(4);
+      if (t == T - 1) STA_TL(5);
+      issue_pv(t);
+      if (t == 0) umma_commit_w(&ou_full);
+      if (t == T - 1) umma_commit_w(&o_full);
+      if (t + 2 < T) {
+        ok = mbar_wait_warp(&k_full[(t + 2) % ST], ((t + 2) / ST) & 1, &dead, p.err, 26);
         if (!ok) break;
         tc_fence_after();
-        issue_pv(1, st, t > 1);
-        if (t + 1 < T) {
-          const int st1 = (t + 1) % ST;
-          ok = mbar_wait_warp(&k_full[st1], ((t + 1) / ST) & 1, &dead, p.err, 27);
-          if (!ok) break;
-          tc_fence_after();
-          issue_qk(1, st1);
-        } else {
-          umma_commit_w(&o_full[1]);
-        }
+        issue_qk(t + 2);
       }
     }
   } else {
-    // ===================================== softmax / epilogue ================================
-    const int r = (warp - 2) >> 2;  // 0 = unconditional row, 1 = conditional row
-    const int row = q0 + ((warp & 3) << 5) + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
-    const uint32_t s_addr = lane_addr + r * Cfg::TMEM_S;
-    const int t_begin = r == 0 ? 0 : 1, t_end = r == 0 ? 1 : T;
-    float sigma = 0.f;  // sum_i m_i c_i of this pixel
+    // ===================================== softmax warpgroups / epilogue =====================================
+    const int g = (warp - 1) >> 2;  // warpgroup: 0 = even tasks + unconditional output, 1 = odd tasks + conditional output
+    const int quad = warp & 3;      // TMEM lane quadrant this warp may access
+    const int row = q0 + (quad << 5) + lane;
+    const bool row_ok = row < n;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad << 5) << 16);
+    const uint32_t s_addr = lane_addr + g * 80;
+
+    // object membership of this pixel (bit i) and sigma = sum_i m_i c_i
+    unsigned int bits = 0;
+    float sigma = 0.f;
+#pragma unroll
+    for (int i = 0; i < kXMaxObj; ++i) {
+      if (i < n_obj) {
+        const bool mk = row_ok && p.mask[((long long)pr * n_obj + i) * n + row] != 0;
+        if (mk) { bits |= 1u << i; sigma += p.coef[pr * n_obj + i]; }
+      }
+    }
+
     bool ok = true;
-    for (int t = t_begin; t < t_end; ++t) {
+    for (int t = g; t < T; t += 2) {
       const int slot = tile_slot[t];
       float w = 1.f;
+      bool live = true;
       if (slot >= 2) {
-        const int i = slot - 2;
-        const float mk = row < n ? (float)p.mask[((long long)pr * n_obj + i) * n + row] : 0.f;
-        w = mk * p.coef[pr * n_obj + i];
-        sigma += w;
+        const bool mk = (bits >> (slot - 2)) & 1u;
+        w = mk ? p.coef[pr * n_obj + slot - 2] : 0.f;
+        live = __any_sync(0xffffffffu, mk);
       }
-      ok = mbar_wait_warp(&s_full[r], (t - t_begin) & 1, &dead, p.err, 30);
+      ok = mbar_wait_warp(&s_full[g], (t >> 1) & 1, &dead, p.err, 30);
       if (!ok) break;
       tc_fence_after();
-      uint32_t s[80];
-      tmem_ld32(s_addr, s);
-      tmem_ld32(s_addr + 32, s + 32);
-      tmem_ld16(s_addr + 64, s + 64);
-      tmem_ld_wait();
-      const int valid = p.ctx_len;
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (warp == 1 && t == 0) STA_TL(6);
+      if (warp == 5 && t == 1) STA_TL(7);
+      if (live) {
+        uint32_t s[80];
+        tmem_ld32(s_addr, s);
+        tmem_ld32(s_addr + 32, s + 32);
+        tmem_ld16(s_addr + 64, s + 64);
+        tmem_ld_wait();
+        const int valid = p.ctx_len;
+        if (valid >= 76) {  // CLIP's 77 tokens: only the last columns are padding
 #pragma unroll
-      for (int c = 0; c < 80; c += 2) {
-        if (c >= valid) s[c] = 0xff800000u;
-        if (c + 1 >= valid) s[c + 1] = 0xff800000u;
-        mx0 = fmaxf(mx0, __uint_as_float(s[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+          for (int c = 76; c < 80; ++c)
+            if (c >= valid) s[c] = 0xff800000u;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 76; ++c)
+            if (c >= valid) s[c] = 0xff800000u;
+#pragma unroll
+          for (int c = 76; c < 80; ++c) s[c] = 0xff800000u;
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 80; c += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+        }
+        const float m = fmaxf(mx0, mx1) * p.scale_log2;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 80; c += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2, -m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -m));
+          l0 += p0;
+          l1 += p1;
+          s[c] = __float_as_uint(p0);
+          s[c + 1] = __float_as_uint(p1);
+        }
+        const float l = l0 + l1;
+        const float f = __fdividef(w, l);
+#pragma unroll
+        for (int c0 = 0; c0 < 80; c0 += 16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pk[i] = pack_half2(__uint_as_float(s[c0 + 2 * i]) * f, __uint_as_float(s[c0 + 2 * i + 1]) * f);
+          tmem_st8(s_addr + (c0 >> 1), pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g]);
+        if (warp == 1 && t == 0) STA_TL(8);
+        if (warp == 5 && t == 1) STA_TL(9);
+        if (p.lse && row_ok)
+          p.lse[(((long long)pr * p.heads + h) * n_slots + slot) * n + row] = (m + log2f(l)) * 0.6931471805599453f;
+      } else {
+        uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int c0 = 0; c0 < 40; c0 += 8) tmem_st8(s_addr + c0, z);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g]);
       }
-      const float m = fmaxf(mx0, mx1) * p.scale_log2;
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 80; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2, -m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -m));
-        l0 += p0;
-        l1 += p1;
-        s[c] = __float_as_uint(p0);
-        s[c + 1] = __float_as_uint(p1);
-      }
-      const float l = l0 + l1;
-      const float f = w / l;
-#pragma unroll
-      for (int c0 = 0; c0 < 80; c0 += 16) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          pk[i] = pack_half2(__uint_as_float(s[c0 + 2 * i]) * f, __uint_as_float(s[c0 + 2 * i + 1]) * f);
-        tmem_st8(s_addr + (c0 >> 1), pk);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[r]);
-      if (p.lse && row < n)
-        p.lse[(((long long)pr * p.heads + h) * n_slots + slot) * n + row] = (m + log2f(l)) * 0.6931471805599453f;
     }
-    // -------- epilogue --------
+    // -------- epilogue: warpgroup 0 stores the unconditional row, warpgroup 1 the conditional row --------
     ok = __all_sync(0xffffffffu, ok);
-    if (ok) ok = mbar_wait_warp(&o_full[0], 0, &dead, p.err, 31);
-    if (ok && r == 1) ok = mbar_wait_warp(&o_full[1], 0, &dead, p.err, 32);
+    if (ok) ok = g == 0 ? mbar_wait_warp(&ou_full, 0, &dead, p.err, 31) : mbar_wait_warp(&o_full, 0, &dead, p.err, 32);
+    if (warp == 1) STA_TL(10);
+    if (warp == 5) STA_TL(11);
     if (ok) {
       tc_fence_after();
       const uint32_t ou_addr = lane_addr + Cfg::TMEM_O;
       const uint32_t oc_addr = ou_addr + DMMA;
-      __half* orow = p.out + (long long)(pr + r * B) * p.o_batch_stride + (long long)row * p.o_token_stride + h * D;
+      __half* orow = p.out + (long long)(pr + g * B) * p.o_batch_stride + (long long)row * p.o_token_stride + h * D;
 #pragma unroll
       for (int c0 = 0; c0 < D; c0 += 8) {
         uint32_t u[8], c[8];
         tmem_ld8(ou_addr + c0, u);
-        if (r == 1) tmem_ld8(oc_addr + c0, c);
+        if (g == 1) tmem_ld8(oc_addr + c0, c);
         tmem_ld_wait();
         float o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          o[i] = r == 0 ? __uint_as_float(u[i]) : fmaf(-sigma, __uint_as_float(u[i]), __uint_as_float(c[i]));
-        if (row < n) {
+          o[i] = g == 0 ? __uint_as_float(u[i]) : fmaf(-sigma, __uint_as_float(u[i]), __uint_as_float(c[i]));
+        if (row_ok) {
           uint4 v;
           v.x = pack_half2(o[0], o[1]);
           v.y = pack_half2(o[2], o[3]);
@@ -293,9 +384,19 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
     }
   }
+  if (warp == 1) STA_TL(12);
+  if (warp == 5) STA_TL(13);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_COLS);
+  if (warp == 1) STA_TL(14);
+#ifdef STA_TIMELINE
+  if (p.tl && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.tl[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 15] = (long long)gt;
+  }
+#endif
 }
 
 template <int D>
@@ -321,6 +422,9 @@ static int launch_xattn_fwd(const sta_xattn_fwd_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   XattnFwdParams p;
+#ifdef STA_TIMELINE
+  p.tl = g_timeline_fwd;
+#endif
   p.mask = a->mask;
   p.coef = a->coef;
   p.out = reinterpret_cast<__half*>(a->out);
@@ -334,11 +438,11 @@ static int launch_xattn_fwd(const sta_xattn_fwd_args* a, cudaStream_t stream) {
   p.o_batch_stride = a->o_batch_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.err = device_error_word();
-  static bool attr_set = false;
-  if (!attr_set) {
-    STA_CUDA_CHECK(cudaFuncSetAttribute(xattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce smem_attr;
+  int rc = smem_attr.run([] {
+    return cudaFuncSetAttribute(xattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  if (rc) return rc;
   dim3 grid((a->n + 127) / 128, a->heads, a->prompts);
   xattn_fwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_k, tm_v, p);
   STA_CUDA_CHECK(cudaGetLastError());
@@ -346,6 +450,10 @@ static int launch_xattn_fwd(const sta_xattn_fwd_args* a, cudaStream_t stream) {
 }
 
 }  // namespace sta
+
+#ifdef STA_TIMELINE
+extern "C" void sta_debug_timeline_fwd(long long* dev) { sta::g_timeline_fwd = dev; }
+#endif
 
 extern "C" int sta_xattn_fwd(const sta_xattn_fwd_args* a, void* stream) {
   using namespace sta;

@@ -82,6 +82,7 @@ class XattnBwdArgs(C.Structure):
         ("q_token_stride", C.c_int64), ("q_batch_stride", C.c_int64),
         ("do_token_stride", C.c_int64), ("do_batch_stride", C.c_int64),
         ("scale", C.c_float),
+        ("out", C.c_void_p), ("o_token_stride", C.c_int64), ("o_batch_stride", C.c_int64),
     ]
 
 

@@ -153,7 +153,8 @@ def xattn_fwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: O
         if tuple(coef.shape) != (B, n_obj) or not coef.is_contiguous():
             raise RuntimeError(f"coef must be contiguous float32 [{B}, {n_obj}], got {tuple(coef.shape)}")
     out = torch.empty((b2, n, c), device=q.device, dtype=torch.float16)
-    lse = torch.zeros((B, heads, 2 + n_obj, n), device=q.device, dtype=torch.float32) if need_lse else None
+    # only the entries the forward evaluates are ever read by the backward (see include/sta_b200.h): no zero-fill node
+    lse = torch.empty((B, heads, 2 + n_obj, n), device=q.device, dtype=torch.float32) if need_lse else None
     a = native.XattnFwdArgs()
     a.q, a.k_ctx, a.v_ctx, a.out = q.data_ptr(), k_ctx.data_ptr(), v_ctx.data_ptr(), out.data_ptr()
     a.mask = mask.data_ptr() if n_obj > 0 else None
@@ -171,11 +172,16 @@ def xattn_fwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: O
 
 def xattn_bwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: Optional[torch.Tensor],
               coef: Optional[torch.Tensor], lse: torch.Tensor, d_out: torch.Tensor, heads: int,
-              scale: Optional[float] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """Backward of xattn_fwd: returns (d_q fp16 [2B, n, C], d_coef f32 [B, n_obj] | None)."""
+              scale: Optional[float] = None, out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Backward of xattn_fwd: returns (d_q fp16 [2B, n, C], d_coef f32 [B, n_obj] | None).  `out` is the forward's
+    output (required when there are objects: its unconditional rows give delta_uc for d_coef)."""
     _require(q, "q")
     _require(d_out, "d_out")
     _require(lse, "lse", torch.float32)
+    if k_ctx.shape[1] > 2:
+        if out is None:
+            raise RuntimeError("xattn_bwd needs the forward output `out` when n_obj > 0")
+        _require(out, "out")
     b2, n, c = q.shape
     B = b2 // 2
     n_obj, ctx_len = k_ctx.shape[1] - 2, k_ctx.shape[2]
@@ -193,6 +199,9 @@ def xattn_bwd(q: torch.Tensor, k_ctx: torch.Tensor, v_ctx: torch.Tensor, mask: O
     a.q_token_stride, a.q_batch_stride = _token_major(q, "q")
     a.do_token_stride, a.do_batch_stride = _token_major(d_out, "d_out")
     a.scale = scale
+    if out is not None:
+        a.out = out.data_ptr()
+        a.o_token_stride, a.o_batch_stride = _token_major(out, "out")
     with _timed("xattn_bwd", (B, n, heads, d, n_obj)):
         native.check(native.load().sta_xattn_bwd(C.byref(a), _stream()), "sta_xattn_bwd")
     LAUNCHES["xattn_bwd"] += 1
@@ -271,16 +280,16 @@ class DualCrossAttentionFn(torch.autograd.Function):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[4]
         out, lse = xattn_fwd(q, k_ctx, v_ctx, mask, coef, heads, need_lse=need)
         if need:
-            ctx.save_for_backward(q, k_ctx, v_ctx, mask, coef, lse)
+            ctx.save_for_backward(q, k_ctx, v_ctx, mask, coef, lse, out)
             ctx.heads = heads
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        q, k_ctx, v_ctx, mask, coef, lse = ctx.saved_tensors
+        q, k_ctx, v_ctx, mask, coef, lse, out = ctx.saved_tensors
         if d_out.stride(2) != 1:
             d_out = d_out.contiguous()
-        d_q, d_coef = xattn_bwd(q, k_ctx, v_ctx, mask, coef, lse, d_out.to(torch.float16), ctx.heads)
+        d_q, d_coef = xattn_bwd(q, k_ctx, v_ctx, mask, coef, lse, d_out.to(torch.float16), ctx.heads, out=out)
         return d_q, None, None, None, d_coef, None
 
 

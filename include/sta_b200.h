@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define STA_B200_VERSION 100 /* major*100 + minor */
+#define STA_B200_VERSION 101 /* major*100 + minor */
 
 /* return codes */
 #define STA_OK 0
@@ -106,7 +106,9 @@ int sta_sattn_bwd(const sta_sattn_bwd_args* args, void* stream);
  *   mask     u8   [B, n_obj, n]     1 inside object i's disc (attention.py:254-261), else 0
  *   coef     f32  [B, n_obj]        alpha_i for this timestep (plms.py:243, weighting_parameter[:, i])
  *   out      fp16 [2*B, n, heads*head_dim]   pre-`to_out` blended attention output
- *   lse      f32  [B, heads, 2 + n_obj, n]   optional (NULL for inference); slot order as k_ctx
+ *   lse      f32  [B, heads, 2 + n_obj, n]   optional (NULL for inference); slot order as k_ctx.  Written for slots
+ *                                            0 and 1 everywhere and for slot 2+i on every aligned run of 32 pixels that
+ *                                            touches object i's mask (the only places the backward reads it).
  * ctx_len <= 80 (77 for CLIP).  n_obj in [0, 8].
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -141,6 +143,10 @@ typedef struct {
   int64_t q_token_stride, q_batch_stride;
   int64_t do_token_stride, do_batch_stride;
   float scale;
+  /* the forward's `out` (fp16 [2*B, n, heads*head_dim], strides in elements): its unconditional rows ARE A_u, which
+   * gives delta_uc = <d_out_c, A_u> for d(coef) without a third accumulator.  Required when n_obj > 0. */
+  const void* out;
+  int64_t o_token_stride, o_batch_stride;
 } sta_xattn_bwd_args;
 
 int sta_xattn_bwd(const sta_xattn_bwd_args* args, void* stream);
