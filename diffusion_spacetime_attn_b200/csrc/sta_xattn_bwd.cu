@@ -66,7 +66,7 @@ template <int D>
 __global__ void __launch_bounds__(XattnBwdCfg<D>::THREADS, XattnBwdCfg<D>::MIN_CTAS)
 xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_do,
                  const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                 const XattnBwdParams p) {
+                 const __grid_constant__ CUtensorMap tm_dq, const XattnBwdParams p) {
   using Cfg = XattnBwdCfg<D>;
   constexpr int ST = Cfg::ST, NBLK = Cfg::NBLK, DMMA = Cfg::DMMA, NBUF = Cfg::NBUF;
   constexpr bool SEPQ = Cfg::SEPQ;
@@ -83,7 +83,8 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   __shared__ uint64_t qu_full, do_full, qc_full, su_done, dau_ready;
   __shared__ uint64_t k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
-  __shared__ uint64_t sdp_full[NBUF], ds_ready[NBUF], dqu_full, dqc_full;
+  __shared__ uint64_t sdp_full[NBUF], ds_ready[NBUF], dqu_full, dqc_full, list_ready;
+  __shared__ unsigned int tile_bits_s;
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
   __shared__ int tile_slot[2 + kBMaxObj];
@@ -113,6 +114,8 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       dead = 0;
+      tile_bits_s = 0;
+      mbar_init(&list_ready, 1);
       mbar_init(&qu_full, 1);
       mbar_init(&do_full, 1);
       mbar_init(&qc_full, 1);
@@ -141,31 +144,6 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       load_q(sQc, &tm_q, &qc_full, pr + B);
     }
     if (ST >= 2) { load_k(1, 1); load_v(1, 1); }
-    // which objects touch this pixel tile?
-    int cnt = 2;
-    if (lane == 0) { tile_slot[0] = 0; tile_slot[1] = 1; }
-    unsigned int any[kBMaxObj];
-#pragma unroll
-    for (int i = 0; i < kBMaxObj; ++i) {
-      any[i] = 0;
-      if (i < n_obj) {
-        const uint8_t* m = p.mask + ((long long)pr * n_obj + i) * n + q0;
-        if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 3) == 0) && q0 + lane * 4 + 3 < n) {
-          any[i] = *reinterpret_cast<const unsigned int*>(m + lane * 4);
-        } else {
-          for (int j = 0; j < 4; ++j)
-            if (q0 + lane * 4 + j < n) any[i] |= m[lane * 4 + j];
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kBMaxObj; ++i) {
-      if (i < n_obj && __any_sync(0xffffffffu, any[i] != 0)) {
-        if (lane == 0) tile_slot[cnt] = 2 + i;
-        ++cnt;
-      }
-    }
-    if (lane == 0) n_tiles_s = cnt;
   } else if (warp == 1) {
     tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
     tmem_relinquish();
@@ -174,7 +152,6 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const int T = n_tiles_s;
 
   if (warp == 0) {
     // ===================================== control warp: TMA + MMA issue =====================================
@@ -204,8 +181,7 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       umma_commit_w(&k_empty[st]);
     };
 
-    int k_next = T < ST ? T : ST, v_next = k_next;
-    for (int t = 2; t < k_next; ++t) { load_k(t, tile_slot[t]); load_v(t, tile_slot[t]); }
+    int T = 2, k_next = ST < 2 ? ST : 2, v_next = k_next;  // tasks 0 / 1 always exist; the rest once the list is known
     int sdp_issued = 0, dq_issued = 0;
     bool ok = true;
 
@@ -247,6 +223,13 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           load_q(sQc, &tm_q, &qc_full, pr + B);
         }
       }
+    }
+    if (ok) ok = mbar_wait_warp(&list_ready, 0, &dead, p.err, 28);  // built by warpgroup 0 while the loads are in flight
+    if (ok) {
+      T = n_tiles_s;
+      const int first = k_next;
+      k_next = v_next = T < ST ? T : ST;
+      for (int t = first; t < k_next; ++t) { load_k(t, tile_slot[t]); load_v(t, tile_slot[t]); }
     }
     if (ok) ok = mbar_wait_warp(&dau_ready, 0, &dead, p.err, 22) && mbar_wait_warp(&v_full[0], 0, &dead, p.err, 26);
     if (ok) {
@@ -294,6 +277,23 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
     }
 
+    if (g == 0) {
+      // task list: tile-level union of the four warps' membership bits (warpgroup 0 covers all 128 pixels)
+      const unsigned int wbits = __reduce_or_sync(0xffffffffu, bits);
+      if (lane == 0) atomicOr(&tile_bits_s, wbits);
+      named_bar_sync(1, 128);
+      if (warp == 1 && lane == 0) {
+        const unsigned int tb = tile_bits_s;
+        int cnt = 2;
+        tile_slot[0] = 0;
+        tile_slot[1] = 1;
+        for (int i = 0; i < n_obj; ++i)
+          if ((tb >> i) & 1u) tile_slot[cnt++] = 2 + i;
+        n_tiles_s = cnt;
+        mbar_arrive(&list_ready);  // release: the list is visible to whoever observes the phase flip
+      }
+    }
+
     bool ok = true;
     float delta_uc = 0.f;
     if (n_obj > 0 || g == 0) ok = mbar_wait_warp(&do_full, 0, &dead, p.err, 29);
@@ -338,26 +338,37 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       if (lane == 0) mbar_arrive(&dau_ready);
     }
 
-    auto write_dq = [&](int batch_row, uint32_t col) {
-      __half* drow = p.d_q + ((long long)batch_row * n + row) * (p.heads * D) + h * D;
+    // dQ (fp32, TMEM) -> fp16 -> a dead operand tile in the TMA swizzled layout -> one TMA store per 64 channels
+    // (full-line writes instead of 16 bytes per 2*C-byte-strided row per thread)
+    auto write_dq = [&](int batch_row, uint32_t col, unsigned char* stage, int bar_id) {
 #pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 8) {
-        uint32_t o[8];
-        tmem_ld8(lane_addr + col + c0, o);
+      for (int c0 = 0; c0 < DMMA; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld16(lane_addr + col + c0, o);
         tmem_ld_wait();
-        if (row_ok) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
           uint4 v;
-          v.x = pack_half2(__uint_as_float(o[0]), __uint_as_float(o[1]));
-          v.y = pack_half2(__uint_as_float(o[2]), __uint_as_float(o[3]));
-          v.z = pack_half2(__uint_as_float(o[4]), __uint_as_float(o[5]));
-          v.w = pack_half2(__uint_as_float(o[6]), __uint_as_float(o[7]));
-          *reinterpret_cast<uint4*>(drow + c0) = v;
+          v.x = pack_half2(__uint_as_float(o[hh * 8 + 0]), __uint_as_float(o[hh * 8 + 1]));
+          v.y = pack_half2(__uint_as_float(o[hh * 8 + 2]), __uint_as_float(o[hh * 8 + 3]));
+          v.z = pack_half2(__uint_as_float(o[hh * 8 + 4]), __uint_as_float(o[hh * 8 + 5]));
+          v.w = pack_half2(__uint_as_float(o[hh * 8 + 6]), __uint_as_float(o[hh * 8 + 7]));
+          const int ch = (c0 >> 3) + hh;
+          *reinterpret_cast<uint4*>(stage + (ch >> 3) * kBQBlockBytes + sw128_offset(r, ch & 7)) = v;
         }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 128);
+      if (quad == 0 && lane == 0) {  // one thread issues, commits and waits (bulk groups are per thread)
+        for (int blk = 0; blk < NBLK; ++blk) tma_store_4d(&tm_dq, stage + blk * kBQBlockBytes, blk * 64, h, q0, batch_row);
+        bulk_commit_group();
+        bulk_wait_group_read0();
       }
     };
 
+    int T = 2;  // tasks 0 / 1 always exist; the real count is read once this warpgroup's first task is done
     for (int t = g; t < T && ok; t += NBUF) {
-      const int slot = tile_slot[t];
+      const int slot = t >= 2 ? tile_slot[t] : t;
       const uint32_t s_addr = lane_addr + (t % NBUF) * 160;
       float w = 1.f;
       bool mk = false, live = true;
@@ -431,8 +442,12 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         ok = mbar_wait_warp(&dqu_full, 0, &dead, p.err, 31);
         if (ok) {
           tc_fence_after();
-          write_dq(pr, Cfg::TMEM_DQ);
+          write_dq(pr, Cfg::TMEM_DQ, sDOu, 2);  // the dA_u tile is dead once dP_u has been formed
         }
+      }
+      if (ok && t < 2) {
+        ok = mbar_wait_warp(&list_ready, 0, &dead, p.err, 34);
+        if (ok) T = n_tiles_s;
       }
     }
     ok = __all_sync(0xffffffffu, ok);
@@ -440,7 +455,7 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       if (ok) ok = mbar_wait_warp(&dqc_full, 0, &dead, p.err, 33);
       if (ok) {
         tc_fence_after();
-        write_dq(pr + B, Cfg::TMEM_DQ + DMMA);
+        write_dq(pr + B, Cfg::TMEM_DQ + DMMA, sDOc, 3);  // every MMA has completed: dO_c is dead
       }
     }
   }
@@ -453,7 +468,7 @@ xattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 template <int D>
 static int launch_xattn_bwd(const sta_xattn_bwd_args* a, cudaStream_t stream) {
   using Cfg = XattnBwdCfg<D>;
-  CUtensorMap tm_q, tm_do, tm_k, tm_v;
+  CUtensorMap tm_q, tm_do, tm_k, tm_v, tm_dq;
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->heads, (uint64_t)a->n, (uint64_t)a->prompts * 2};
     const uint32_t box[4] = {64, 1, 128, 1};
@@ -462,6 +477,10 @@ static int launch_xattn_bwd(const sta_xattn_bwd_args* a, cudaStream_t stream) {
     if (rc) return rc;
     const uint64_t st2[4] = {2, (uint64_t)D * 2, (uint64_t)a->do_token_stride * 2, (uint64_t)a->do_batch_stride * 2};
     rc = make_tmap_f16(&tm_do, a->d_out, 4, dims, st2, box);
+    if (rc) return rc;
+    const uint64_t C = (uint64_t)a->heads * D;
+    const uint64_t st3[4] = {2, (uint64_t)D * 2, C * 2, C * 2 * (uint64_t)a->n};  // d_q is dense [2B, n, heads*D]
+    rc = make_tmap_f16(&tm_dq, a->d_q, 4, dims, st3, box);
     if (rc) return rc;
   }
   {
@@ -500,7 +519,7 @@ static int launch_xattn_bwd(const sta_xattn_bwd_args* a, cudaStream_t stream) {
   if (a->n_obj > 0)
     STA_CUDA_CHECK(cudaMemsetAsync(a->d_coef, 0, sizeof(float) * a->prompts * a->n_obj, stream));
   dim3 grid((a->n + 127) / 128, a->heads, a->prompts);
-  xattn_bwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_do, tm_k, tm_v, p);
+  xattn_bwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_do, tm_k, tm_v, tm_dq, p);
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }

@@ -59,7 +59,7 @@ static long long* g_timeline_fwd = nullptr;
 #define STA_TL(i)                                                                                     \
   do {                                                                                                \
     if (p.tl && lane == 0)                                                                            \
-      p.tl[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = clock64(); \
+      p.tl[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 20 + (i)] = clock64(); \
   } while (0)
 #else
 #define STA_TL(i) \
@@ -84,7 +84,8 @@ struct XattnFwdParams {
 template <int D>
 __global__ void __launch_bounds__(XattnCfg<D>::THREADS, XattnCfg<D>::MIN_CTAS)
 xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                 const __grid_constant__ CUtensorMap tm_v, const XattnFwdParams p) {
+                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
+                 const XattnFwdParams p) {
   using Cfg = XattnCfg<D>;
   constexpr int ST = Cfg::ST, NBLK = Cfg::NBLK, DMMA = Cfg::DMMA;
 
@@ -96,7 +97,8 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   unsigned char* sV = sK + ST * Cfg::CTILE;
 
   __shared__ uint64_t qu_full, qc_full, k_full[ST], k_empty[ST], v_full[ST], v_empty[ST];
-  __shared__ uint64_t s_full[2], p_ready[2], ou_full, o_full;
+  __shared__ uint64_t s_full[2], p_ready[2], ou_full, o_full, list_ready;
+  __shared__ unsigned int tile_bits_s;
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
   __shared__ int tile_slot[2 + kXMaxObj];  // context slot of the t-th task of this CTA
@@ -106,6 +108,17 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int q0 = blockIdx.x * 128, h = blockIdx.y, pr = blockIdx.z;
   const int n = p.n, B = p.prompts, n_obj = p.n_obj, n_slots = 2 + p.n_obj;
   if (warp == 0) STA_TL(0);
+#ifdef STA_TIMELINE
+  if (p.tl && tid == 0) {
+    unsigned long long gt;
+    unsigned int smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    long long* e = p.tl + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 20;
+    e[16] = (long long)gt;
+    e[17] = smid;
+  }
+#endif
 
   auto load_k = [&](int t, int slot) {
     const int st = t % ST;
@@ -123,8 +136,10 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       dead = 0;
+      tile_bits_s = 0;
       mbar_init(&qu_full, 1);
       mbar_init(&qc_full, 1);
+      mbar_init(&list_ready, 1);
       for (int i = 0; i < ST; ++i) {
         mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
         mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
@@ -142,44 +157,16 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     mbar_expect_tx_w(&qc_full, Cfg::QTILE);
     for (int blk = 0; blk < NBLK; ++blk)
       tma_load_4d_w(sQ + (NBLK + blk) * kXQBlockBytes, &tm_q, &qc_full, blk * 64, h, q0, pr + B);
-    load_k(1, 1);
-    load_v(0, 0);
-    load_v(1, 1);
+    load_k(1, 1);  // V_0 / V_1 follow the first two QK^T issues: the operands on the critical path land first
     STA_TL(1);
-    // which objects touch this pixel tile?  (128 mask bytes per object: one 4-byte word per lane)
-    int cnt = 2;
-    if (lane == 0) { tile_slot[0] = 0; tile_slot[1] = 1; }
-    unsigned int any[kXMaxObj];
-#pragma unroll
-    for (int i = 0; i < kXMaxObj; ++i) {
-      any[i] = 0;
-      if (i < n_obj) {
-        const uint8_t* m = p.mask + ((long long)pr * n_obj + i) * n + q0;
-        if (((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 3) == 0) && q0 + lane * 4 + 3 < n) {
-          any[i] = *reinterpret_cast<const unsigned int*>(m + lane * 4);
-        } else {
-          for (int j = 0; j < 4; ++j)
-            if (q0 + lane * 4 + j < n) any[i] |= m[lane * 4 + j];
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < kXMaxObj; ++i) {
-      if (i < n_obj && __any_sync(0xffffffffu, any[i] != 0)) {
-        if (lane == 0) tile_slot[cnt] = 2 + i;
-        ++cnt;
-      }
-    }
-    if (lane == 0) n_tiles_s = cnt;
   } else if (warp == 1) {
     tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // barriers initialised, TMEM address published: nothing slow (no global load) sits in front of it
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const int T = n_tiles_s;  // task 0 -> unconditional row, tasks 1..T-1 -> conditional row
   if (warp == 0) STA_TL(2);
 
   if (warp == 0) {
@@ -212,20 +199,25 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       umma_commit_w(&v_empty[st]);
     };
 
-    int k_next = T < ST ? T : ST, v_next = k_next;
-    for (int t = 2; t < k_next; ++t) { load_k(t, tile_slot[t]); load_v(t, tile_slot[t]); }
-
     bool ok = mbar_wait_warp(&qu_full, 0, &dead, p.err, 20) && mbar_wait_warp(&k_full[0], 0, &dead, p.err, 21);
     STA_TL(3);
     if (ok) {
       tc_fence_after();
       issue_qk(0);
+      STA_TL(18);
       ok = mbar_wait_warp(&qc_full, 0, &dead, p.err, 22) && mbar_wait_warp(&k_full[1], 0, &dead, p.err, 23);
     }
     if (ok) {
       tc_fence_after();
       issue_qk(1);
+      load_v(0, 0);
+      load_v(1, 1);
+      // the task list (which objects touch this tile) is built by warp 2 while the first loads are in flight
+      ok = mbar_wait_warp(&list_ready, 0, &dead, p.err, 28);
     }
+    const int T = ok ? n_tiles_s : 0;  // task 0 -> unconditional row, tasks 1..T-1 -> conditional row
+    int k_next = T < ST ? T : ST, v_next = k_next;
+    for (int t = 2; t < k_next; ++t) { load_k(t, tile_slot[t]); load_v(t, tile_slot[t]); }
     for (int t = 0; t < T && ok; ++t) {
       // ring refills whose predecessor MMA was issued at least one iteration ago (their completion is imminent)
       while (ok && k_next < T && k_next - ST <= t + 1) {
@@ -274,10 +266,28 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (mk) { bits |= 1u << i; sigma += p.coef[pr * n_obj + i]; }
       }
     }
+    if (g == 0) {
+      // task list: tile-level union of the four warps' membership bits (warpgroup 0 covers all 128 pixels)
+      const unsigned int wbits = __reduce_or_sync(0xffffffffu, bits);
+      if (lane == 0) atomicOr(&tile_bits_s, wbits);
+      named_bar_sync(1, 128);
+      if (warp == 1 && lane == 0) {
+        const unsigned int tb = tile_bits_s;
+        int cnt = 2;
+        tile_slot[0] = 0;
+        tile_slot[1] = 1;
+        for (int i = 0; i < n_obj; ++i)
+          if ((tb >> i) & 1u) tile_slot[cnt++] = 2 + i;
+        n_tiles_s = cnt;
+        mbar_arrive(&list_ready);  // release: the list is visible to whoever observes the phase flip
+      }
+    }
 
     bool ok = true;
+    int T = 2;
     for (int t = g; t < T; t += 2) {
-      const int slot = tile_slot[t];
+      // tasks 0 / 1 (unconditional / global context) always exist; the list is only needed beyond them
+      const int slot = t >= 2 ? tile_slot[t] : t;
       float w = 1.f;
       bool live = true;
       if (slot >= 2) {
@@ -352,6 +362,11 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[g]);
       }
+      if (t < 2) {  // first task done: learn how many tasks this tile has
+        ok = mbar_wait_warp(&list_ready, 0, &dead, p.err, 33);
+        if (!ok) break;
+        T = n_tiles_s;
+      }
     }
     // -------- epilogue: warpgroup 0 stores the unconditional row, warpgroup 1 the conditional row --------
     ok = __all_sync(0xffffffffu, ok);
@@ -360,27 +375,40 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (warp == 5) STA_TL(11);
     if (ok) {
       tc_fence_after();
+      // O (fp32, TMEM) -> fp16 -> the warpgroup's own (dead) Q tile in the TMA swizzled layout -> one TMA store per 64
+      // channels: full-line writes instead of 16 bytes per 2*C-byte-strided row per thread
       const uint32_t ou_addr = lane_addr + Cfg::TMEM_O;
       const uint32_t oc_addr = ou_addr + DMMA;
-      __half* orow = p.out + (long long)(pr + g * B) * p.o_batch_stride + (long long)row * p.o_token_stride + h * D;
+      unsigned char* stage = sQ + g * Cfg::QTILE;
+      const int r = (quad << 5) + lane;
 #pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 8) {
-        uint32_t u[8], c[8];
-        tmem_ld8(ou_addr + c0, u);
-        if (g == 1) tmem_ld8(oc_addr + c0, c);
+      for (int c0 = 0; c0 < DMMA; c0 += 16) {
+        uint32_t u[16], c[16];
+        tmem_ld16(ou_addr + c0, u);
+        if (g == 1) tmem_ld16(oc_addr + c0, c);
         tmem_ld_wait();
-        float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o[i] = g == 0 ? __uint_as_float(u[i]) : fmaf(-sigma, __uint_as_float(u[i]), __uint_as_float(c[i]));
-        if (row_ok) {
+        for (int hh = 0; hh < 2; ++hh) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] = g == 0 ? __uint_as_float(u[hh * 8 + i])
+                          : fmaf(-sigma, __uint_as_float(u[hh * 8 + i]), __uint_as_float(c[hh * 8 + i]));
           uint4 v;
           v.x = pack_half2(o[0], o[1]);
           v.y = pack_half2(o[2], o[3]);
           v.z = pack_half2(o[4], o[5]);
           v.w = pack_half2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(orow + c0) = v;
+          const int ch = (c0 >> 3) + hh;  // 16-byte chunk index along the head dim
+          *reinterpret_cast<uint4*>(stage + (ch >> 3) * kXQBlockBytes + sw128_offset(r, ch & 7)) = v;
         }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2 + g, 128);
+      if (quad == 0 && lane == 0) {  // one thread issues, commits and waits (bulk groups are per thread)
+        for (int blk = 0; blk < NBLK; ++blk) tma_store_4d(&tm_o, stage + blk * kXQBlockBytes, blk * 64, h, q0, pr + g * B);
+        bulk_commit_group();
+        bulk_wait_group_read0();
       }
     }
   }
@@ -394,7 +422,7 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (p.tl && tid == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.tl[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 15] = (long long)gt;
+    p.tl[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 20 + 15] = (long long)gt;
   }
 #endif
 }
@@ -402,12 +430,15 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 template <int D>
 static int launch_xattn_fwd(const sta_xattn_fwd_args* a, cudaStream_t stream) {
   using Cfg = XattnCfg<D>;
-  CUtensorMap tm_q, tm_k, tm_v;
+  CUtensorMap tm_q, tm_k, tm_v, tm_o;
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->heads, (uint64_t)a->n, (uint64_t)a->prompts * 2};
     const uint64_t st[4] = {2, (uint64_t)D * 2, (uint64_t)a->q_token_stride * 2, (uint64_t)a->q_batch_stride * 2};
     const uint32_t box[4] = {64, 1, 128, 1};
     int rc = make_tmap_f16(&tm_q, a->q, 4, dims, st, box);
+    if (rc) return rc;
+    const uint64_t sto[4] = {2, (uint64_t)D * 2, (uint64_t)a->o_token_stride * 2, (uint64_t)a->o_batch_stride * 2};
+    rc = make_tmap_f16(&tm_o, a->out, 4, dims, sto, box);
     if (rc) return rc;
   }
   {
@@ -444,7 +475,7 @@ static int launch_xattn_fwd(const sta_xattn_fwd_args* a, cudaStream_t stream) {
   });
   if (rc) return rc;
   dim3 grid((a->n + 127) / 128, a->heads, a->prompts);
-  xattn_fwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_k, tm_v, p);
+  xattn_fwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_k, tm_v, tm_o, p);
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }

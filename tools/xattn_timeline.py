@@ -25,7 +25,8 @@ def build_debug():
     out = B.BUILD / "libsta_b200_tl.so"
     obj = B.BUILD / "sta_xattn_fwd_tl.o"
     src = B.CSRC / "sta_xattn_fwd.cu"
-    subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DSTA_TIMELINE", "-I", str(B.INCLUDE), "-c", str(src), "-o", str(obj)],
+    extra = [f for f in sys.argv[1:] if f.startswith("-D")]
+    subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DSTA_TIMELINE", *extra, "-I", str(B.INCLUDE), "-c", str(src), "-o", str(obj)],
                    check=True, capture_output=True)
     objs = [str(B.BUILD / (s.stem + ".o")) for s in sorted(B.CSRC.glob("*.cu")) if s.stem != "sta_xattn_fwd"] + [str(obj)]
     subprocess.run([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs], check=True)
@@ -57,7 +58,7 @@ if __name__ == "__main__":
         mask = build_object_masks(boxes, n, "cuda").unsqueeze(0).expand(Bp, -1, -1).contiguous()
         coef = torch.full((Bp, n_obj), 2.5, device="cuda")
         ctas = ((n + 127) // 128) * heads * Bp
-        tl = torch.zeros(ctas, 16, dtype=torch.int64, device="cuda")
+        tl = torch.zeros(ctas, 20, dtype=torch.int64, device="cuda")
         for _ in range(3):
             ops.xattn_fwd(q, kc, vc, mask, coef, heads)
         h.sta_debug_timeline_fwd(C.c_void_p(tl.data_ptr()))
@@ -66,9 +67,22 @@ if __name__ == "__main__":
         h.sta_debug_timeline_fwd(C.c_void_p(0))
         t = tl.cpu()
         rel = (t[:, :15] - t[:, :1]).double()
-        gt = t[:, 15]
-        print(f"== xattn_fwd {(Bp, n, heads, d, n_obj)}: {ctas} CTAs; CTA end-time spread (globaltimer) "
-              f"{(gt.max() - gt.min()).item()} ns")
+        gt, gs, sm = t[:, 15], t[:, 16], t[:, 17]
+        per_sm = torch.bincount(sm, minlength=148)
+        print(f"== xattn_fwd {(Bp, n, heads, d, n_obj)}: {ctas} CTAs on {(per_sm > 0).sum().item()} SMs (max {per_sm.max().item()} per SM); "
+              f"globaltimer: start spread {(gs.max() - gs.min()).item()} ns, end spread {(gt.max() - gt.min()).item()} ns, "
+              f"first start -> last end {(gt.max() - gs.min()).item()} ns")
+        # were two CTAs of one SM resident together?  (second CTA's start before the first one's end)
+        overlap = 0
+        for m in torch.nonzero(per_sm > 1).flatten().tolist():
+            idx = torch.nonzero(sm == m).flatten()
+            st, en = gs[idx], gt[idx]
+            order = torch.argsort(st)
+            if st[order[1]] < en[order[0]]:
+                overlap += 1
+        print(f"   SMs whose first two CTAs overlapped in time: {overlap} of {(per_sm > 1).sum().item()}")
+        c18 = (t[:, 18] - t[:, 0]).double()
+        print(f"   18 qk0_issued      median {c18.median().item():8.0f} cyc")
         for i, nm in enumerate(NAMES):
             col = rel[:, i]
             col = col[t[:, i] != 0]
