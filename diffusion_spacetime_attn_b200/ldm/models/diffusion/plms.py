@@ -166,7 +166,7 @@ class PLMSSampler(object):
             W.requires_grad_(True)
             optimizer = torch.optim.Adam([W], lr=self.lr)
         epochs = self.num_epochs if do_opt else 1
-        losses, img, decoded = [], None, None
+        losses, img, decoded, alpha_grads = [], None, None, []
         for epoch in range(epochs):
             if runner is not None:
                 runner.new_trajectory()
@@ -179,6 +179,7 @@ class PLMSSampler(object):
                     loss, per_prompt = self.loss_fn(decoded, texts, bboxes_pp, names_pp)
                     optimizer.zero_grad(set_to_none=True)
                     loss.backward()
+                    alpha_grads.append(W.grad.detach().clone())  # dL/dalpha of this epoch (diagnostics / parity tests)
                     optimizer.step()
                     losses.append([float(v) for v in torch.stack(per_prompt).detach().cpu()])
             if epoch == epochs - 1 and self.save_images and decoded is not None:
@@ -187,7 +188,7 @@ class PLMSSampler(object):
             runner.active = None
         unet.set_local_contexts(None)
         self.last_result = {"latent": img.detach(), "weighting_parameter": W.detach(), "losses": losses,
-                            "image": decoded.detach() if decoded is not None else None}
+                            "image": decoded.detach() if decoded is not None else None, "alpha_grads": alpha_grads}
         return None
 
     def _save(self, images, epoch, seed, idxs):

@@ -12,10 +12,13 @@ Every function cites the reference file:line it follows; paths are relative to
 Pinning: the reference's own tests hold NO golden vectors for this path.  The oracle is
 therefore pinned against outputs of the UNMODIFIED reference modules imported in the build container by
 `oracle/make_golden.py`; the resulting fixtures live in tests/golden/ and `tests/test_oracle_golden.py`
-re-checks them on every CPU run.  The sampler (plms.py) cannot be imported here (it needs the `clip` package) —
-its arithmetic is restated and checked against a transcription-free property: PLMS with a linear "model" has a
-closed form (tests/test_oracle_sampler.py) — so the SAMPLER part is "parity unpinned by execution", the
-attention/UNet part is pinned by execution of the reference.
+re-checks them on every CPU run.  The sampler arithmetic (`make_schedule`, `plms_update`, `plms_combine`,
+`plms_trajectory`) is pinned the same way: `oracle/make_golden_sampler.py` imports the UNMODIFIED reference
+ldm/models/diffusion/plms.py behind a `clip` shim, runs its own `make_schedule` + `p_sample_plms` for 5 / 10 / 50 steps on
+a linear stand-in UNet, and tests/test_host_cpu.py::test_sampler_pinned_by_execution_of_the_reference_plms compares the
+oracle and the product sampler with that fixture (schedule constants, every e_t, final latent).  Gradients: the
+reference can only back-propagate under CUDA autocast; tools/ref_on_gpu.py runs it there (baseline/_ref) and
+tests/test_ref_gpu_golden.py compares; the oracle's own autograd is pinned by fp64 finite differences.
 """
 from __future__ import annotations
 

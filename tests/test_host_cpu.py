@@ -12,6 +12,10 @@ from diffusion_spacetime_attn_b200.ldm.modules.diffusionmodules import util as U
 from diffusion_spacetime_attn_b200.pipeline import WorkItem, shard_prompts, synthetic_layout
 from oracle import sta_oracle as O
 
+from pathlib import Path
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
 
 @pytest.mark.parametrize("S", [10, 50, 100])
 def test_schedule_matches_oracle(S):
@@ -87,6 +91,63 @@ def test_product_sampler_arithmetic_matches_oracle_on_cpu():
 
     z_ref = O.plms_trajectory(eps_model, x_T, S)
     assert (z - z_ref).abs().max() < 1e-4
+
+
+def _linear_unet_eps(x_in, t_in, c_in, coef):
+    """The linear stand-in UNet of oracle/make_golden_sampler.py (restated: the fixture script is not imported)."""
+    s = (t_in.float() / 1000.0).reshape(-1, 1, 1, 1)
+    k = 1.0 + coef.sum() * 0.01
+    row = torch.cat([torch.zeros_like(x_in[:1]), torch.ones_like(x_in[1:])])
+    return 0.1 * k * x_in * s + 0.02 * torch.roll(x_in, 1, dims=-1) + 0.05 * row * (1.0 + c_in.mean())
+
+
+@pytest.mark.parametrize("S", [5, 10, 50])
+def test_sampler_pinned_by_execution_of_the_reference_plms(S):
+    """tests/golden/plms_sampler.npz holds the output of the UNMODIFIED reference `make_schedule` + `p_sample_plms`
+    (ldm/models/diffusion/plms.py:81-112, 296-358; driven as plms.py:227-247 does) on a linear stand-in UNet.  The oracle's
+    restatement and the product sampler must reproduce the schedule constants, every e_t and the final latent."""
+    from diffusion_spacetime_attn_b200.ldm.models.diffusion.plms import PLMSSampler
+
+    fx = np.load(GOLD / "plms_sampler.npz")
+    g = torch.Generator().manual_seed(S)
+    x_T = torch.randn(1, 4, 8, 8, generator=g)
+    c = torch.randn(1, 77, 768, generator=g)
+    uc = torch.randn(1, 77, 768, generator=g)
+    W = 2.5 + 0.5 * torch.randn(2, S, generator=g)
+    # ---- oracle ----
+    sch = O.make_schedule(S)
+    assert np.array_equal(sch.timesteps, fx[f"S{S}_timesteps"])
+    assert np.allclose(sch.alphas, fx[f"S{S}_alphas"], rtol=1e-6) and np.allclose(sch.alphas_prev, fx[f"S{S}_alphas_prev"], rtol=1e-6)
+    seen = []
+
+    def eps_model(x, t, i):
+        out = _linear_unet_eps(torch.cat([x, x]), torch.full((2,), t), torch.cat([uc, c]), W[:, i])
+        e_u, e_c = out.chunk(2)
+        e = e_u + 7.5 * (e_c - e_u)
+        seen.append(e)
+        return e
+
+    z = O.plms_trajectory(eps_model, x_T, S, sch)
+    ref_z = torch.from_numpy(fx[f"S{S}_latent"])
+    assert (z - ref_z).abs().max().item() < 2e-5 * ref_z.abs().max().item() + 1e-5
+    # e_t of step i: the first step evaluates the model twice (plms.py:341-345), so seen[0], seen[2], seen[3], ...
+    e_hist = torch.stack([seen[0]] + seen[2:])
+    assert (e_hist - torch.from_numpy(fx[f"S{S}_eps"])).abs().max().item() < 2e-5 * float(np.abs(fx[f"S{S}_eps"]).max()) + 1e-5
+
+    # ---- product sampler (host arithmetic only; the stand-in replaces the UNet) ----
+    class FakeModel:
+        num_timesteps = 1000
+        device = torch.device("cpu")
+        alphas_cumprod = torch.tensor(np.cumprod(1.0 - U.make_beta_schedule("linear", 1000, 0.00085, 0.012)), dtype=torch.float32)
+
+        def apply_model_extra(self, x_in, text_index, t_in, c_in, coef=None, bboxs_curr=None, step_time=None):
+            return _linear_unet_eps(x_in, t_in, c_in, coef)
+
+    sampler = PLMSSampler(FakeModel(), clip_loss_model=torch.nn.Identity(), save_images=False)
+    sampler.make_schedule(S, verbose=False)
+    assert np.array_equal(np.asarray(sampler.ddim_timesteps), fx[f"S{S}_timesteps"])
+    zp = sampler._trajectory(x_T.clone(), c, uc, 7.5, W.unsqueeze(0), [[0.3, 0.5], [0.7, 0.5]], 0)
+    assert (zp - ref_z).abs().max().item() < 2e-5 * ref_z.abs().max().item() + 1e-5
 
 
 def test_prompt_readers_and_layout():
