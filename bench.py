@@ -14,11 +14,16 @@ sharded round-robin, no data-path collective (weights broadcast once at start-up
 `value`    images/s with each step's inputs already resident in HBM and the result left on the device.
 `e2e`      the same through the public API (SpaceTimeAttnPipeline.generate) with HOST inputs: every step copies its
            conditioning + x_T from pinned host memory and reads the decoded image back to the host.
-`roofline` the kernel with the largest share of device time inside the timed region, timed per launch with CUDA
-           events on the launching stream; achieved = algorithmic FLOPs per launch / mean launch time; peak = the
-           driver-measured MEASURED_PEAKS.json figure (sustained: the kernel runs inside a long step).
+`roofline` the fused dual cross-attention forward (the kernel BASELINE.json's metric names; HBM/latency-bound, SURVEY.md
+           8d) at its dominant geometry: achieved = algorithmic bytes per launch / mean launch time, peak = the
+           driver-measured copy bandwidth (MEASURED_PEAKS.json), traffic = DRAM bytes of one ncu capture
+           (profiles/roofline_traffic.json).  `roofline_xattn_bwd`, `roofline_sattn`, `roofline_sattn_bwd` beside it (the
+           self-attention kernels are tensor-bound: algorithmic FLOPs against the BURST cuBLAS figure, because in
+           CUDA-graph mode each kernel is timed alone — launches inside a replay cannot be bracketed by events).
 `cpu_baseline` the CPU oracle (a port of the reference algorithm) timed on this box's host cores on a bounded sample
-           (forward and forward+backward UNet evaluations, extrapolated to one alpha-optimised image).
+           (forward and forward+backward UNet evaluations, EXTRAPOLATED to one alpha-optimised image: `extrapolated: true`).
+`reference_on_b200` the UNMODIFIED reference on a B200 under autocast (recorded by tools/ref_on_gpu.py, not re-run).
+`--config K`  BASELINE.json configs[K-1] (default 2 = configs[1], the configuration the metric is quoted on).
 """
 from __future__ import annotations
 
@@ -37,7 +42,33 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "images_per_sec_512x512_50step"
 UNIT = "images/s"
-EVALS_PER_IMAGE = 3 * 51  # 3 alpha epochs x (50 PLMS steps + 1 extra evaluation at the first step)
+
+# BASELINE.json `configs` (1-based here).  --config 2 (default) is the configuration the metric is quoted on; the others
+# produce the lines of BASELINE.md §5 (`python bench.py --config K`, and the same under torchrun for N > 1).
+CONFIGS = {
+    1: dict(workload="BASELINE.json configs[0]: single prompt 'a red cube left of a blue sphere', 2 objects, 64x64 latent, "
+                     "10 PLMS steps, fixed alpha (no inner opt)", metric="images_per_sec_512x512_10step_fixed_alpha",
+            steps=10, epochs=1, optimize=False, latent=64, sampler="plms", batch=1, objects=[2], first_prompt_only=True),
+    2: dict(workload="BASELINE.json configs[1]: SD-v1-4 architecture 512x512, 50 PLMS steps, 2-3 objects, alpha inner-opt on "
+                     "(3 epochs), batch=1 per GPU", metric=METRIC,
+            steps=50, epochs=3, optimize=True, latent=64, sampler="plms", batch=1, objects=None),
+    3: dict(workload="BASELINE.json configs[2]: MS-COCO-style captions with 2-5 objects (mscoco.pkl's distribution 201/149/135/15 "
+                     "of 500, synthetic layouts), 512x512, 50 PLMS steps, alpha inner-opt on, prompt-sharded, batch=1 per GPU",
+            metric=METRIC, steps=50, epochs=3, optimize=True, latent=64, sampler="plms", batch=1,
+            objects=[2, 3, 4, 2, 3, 4, 2, 3, 2, 4, 2, 3, 4, 2, 3, 5]),
+    4: dict(workload="BASELINE.json configs[3]: VSR-style spatial-relation prompts, 512x512, 50 PLMS steps, 4-object masks "
+                     "(2x2 grid), alpha optimised per timestep, batch=1 per GPU", metric=METRIC,
+            steps=50, epochs=3, optimize=True, latent=64, sampler="plms", batch=1, objects=[4]),
+    5: dict(workload="BASELINE.json configs[4]: 768x768 (96x96 latent), 100 DDIM steps (+ injection: an extension, the "
+                     "reference's DDIM has none), 6 local descriptions, alpha inner-opt on, batch=2 per GPU (16 over 8)",
+            metric="images_per_sec_768x768_100step", steps=100, epochs=3, optimize=True, latent=96, sampler="ddim", batch=2,
+            objects=[6]),
+}
+
+
+def evals_per_image(cfg):
+    """UNet evaluations of one image: epochs x (steps + 1 for PLMS: the first step evaluates twice, plms.py:341-345)."""
+    return cfg["epochs"] * (cfg["steps"] + (1 if cfg["sampler"] == "plms" else 0))
 
 
 def parse_args():
@@ -46,12 +77,22 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2, help="timed images per GPU (each ~ seconds)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
-    ap.add_argument("--ddim_steps", type=int, default=50)
-    ap.add_argument("--epochs", type=int, default=3)
+    ap.add_argument("--config", type=int, choices=sorted(CONFIGS), default=2, help="BASELINE.json configs[K-1]")
+    ap.add_argument("--ddim_steps", type=int, default=None, help="override the config's step count (debugging)")
+    ap.add_argument("--epochs", type=int, default=None, help="override the config's alpha epochs (debugging)")
     ap.add_argument("--checkpoint_min_tokens", type=int, default=int(os.environ.get("STA_CKPT_MIN_TOKENS", "0")))
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs (block-level checkpointing, as the reference)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.ddim_steps is not None:
+        cfg["steps"] = args.ddim_steps
+        cfg["workload"] += f" [steps overridden: {args.ddim_steps}]"
+    if args.epochs is not None:
+        cfg["epochs"] = args.epochs
+        cfg["workload"] += f" [epochs overridden: {args.epochs}]"
+    args.cfg = cfg
+    return args
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -195,23 +236,25 @@ def standalone_kernel_ms(kind, key, iters=10):
 # ------------------------------------------------------------------------------------------------------
 # CPU oracle timing (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------------
-def cpu_oracle_images_per_sec(n_evals: int):
-    """Time the CPU oracle (fp32, all host threads) at BASELINE configs[1]'s geometry (batch 2 CFG, 64x64 latent, 2 objects)
-    on a bounded sample — `n_evals` forward UNet evaluations and `n_evals` forward+backward evaluations (gradients w.r.t.
-    the latent and alpha, torch autograd through the out-of-place restatement; the reference itself cannot back-propagate
-    on CPU) — and extrapolate one alpha-optimised image = 3 x 51 forwards + 3 x 50 backwards, WITHOUT the
-    reference's per-block recompute (the favourable reading for the CPU):  t_image = 153 t_fwd + 150 (t_fwd+bwd - t_fwd).
-    Returns (images/s, t_fwd, t_fwd+bwd, cores)."""
+def cpu_oracle_images_per_sec(n_evals: int, cfg):
+    """Time the CPU oracle (fp32, all host threads) at the config's geometry (batch 2 CFG per prompt, its latent size and
+    object count) on a bounded sample — `n_evals` forward UNet evaluations and `n_evals` forward+backward evaluations
+    (gradients w.r.t. the latent and alpha, torch autograd through the out-of-place restatement; the reference itself cannot
+    back-propagate on CPU) — and EXTRAPOLATE one image: E_f t_fwd + E_b (t_fwd+bwd - t_fwd) with E_f / E_b the
+    config's forward / backward evaluation counts, WITHOUT the reference's per-block recompute (the favourable reading for
+    the CPU) and without VAE decode / CLIP loss.  At the 96x96 latent the autograd tape of an evaluation would need > 100 GB of
+    host memory, so there only the forward is timed and the backward is taken as 2 x forward (stated in `sample`).
+    Returns a dict (images/s, times, cores, sample text)."""
     import torch
 
     from oracle import sta_oracle as O
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.UNetConfig()
+    ocfg = O.UNetConfig()
     g = torch.Generator().manual_seed(0)
     p = {}
-    for k, shp in O.unet_param_shapes(cfg).items():  # fast init (values do not matter for timing)
+    for k, shp in O.unet_param_shapes(ocfg).items():  # fast init (values do not matter for timing)
         t = torch.empty(shp)
         if k.endswith("weight") and len(shp) > 1:
             t.normal_(0, (1.0 / max(1, int(torch.tensor(shp[1:]).prod()))) ** 0.5, generator=g)
@@ -220,62 +263,112 @@ def cpu_oracle_images_per_sec(n_evals: int):
         else:
             t.fill_(1.0)
         p[k] = t
-    x = torch.randn(2, 4, 64, 64, generator=g)
+    lat = cfg["latent"]
+    n_obj = (cfg["objects"] or [2])[0]
+    x = torch.randn(2, 4, lat, lat, generator=g)
     ctx = torch.randn(2, 77, 768, generator=g)
-    locs = [torch.randn(2, 77, 768, generator=g) for _ in range(2)]
-    bboxes = [[0.3, 0.5], [0.7, 0.5]]
+    locs = [torch.randn(2, 77, 768, generator=g) for _ in range(n_obj)]
+    bboxes = [[0.25 + 0.5 * (i % 2), 0.25 + 0.25 * (i // 2)] for i in range(n_obj)]
+    coef0 = torch.full((n_obj,), 5.0 / n_obj)
     t_in = torch.full((2,), 501, dtype=torch.long)
     with torch.no_grad():
-        O.unet_forward(x, t_in, ctx, torch.tensor([2.5, 2.5]), bboxes, locs, p, cfg)  # warm-up
+        O.unet_forward(x, t_in, ctx, coef0, bboxes, locs, p, ocfg)  # warm-up
         t0 = time.perf_counter()
         for _ in range(n_evals):
-            O.unet_forward(x, t_in, ctx, torch.tensor([2.5, 2.5]), bboxes, locs, p, cfg)
+            O.unet_forward(x, t_in, ctx, coef0, bboxes, locs, p, ocfg)
         t_f = (time.perf_counter() - t0) / n_evals
-    t0 = time.perf_counter()
-    for _ in range(n_evals):
-        xg = x.clone().requires_grad_(True)
-        coef = torch.tensor([2.5, 2.5], requires_grad=True)
-        y = O.unet_forward(xg, t_in, ctx, coef, bboxes, locs, p, cfg)
-        torch.autograd.grad(y, [xg, coef], torch.ones_like(y))
-    t_fb = (time.perf_counter() - t0) / n_evals
-    t_image = EVALS_PER_IMAGE * t_f + 3 * 50 * max(t_fb - t_f, 0.0)
-    return 1.0 / t_image, t_f, t_fb, cores
-
-
-def _cpu_sample_text(n, t_f, t_fb):
-    return (f"{n} forward and {n} forward+backward UNet evaluation(s) of the CPU oracle (fp32, batch 2, 64x64 latent, 2 objects): "
-            f"{t_f:.2f} s and {t_fb:.2f} s each; one alpha-optimised image extrapolated as 153 t_fwd + 150 (t_fwd+bwd - t_fwd), "
-            "no per-block recompute (the reference has no working CPU backward; this is the oracle port's autograd)")
+    bwd_timed = lat <= 64
+    if bwd_timed:
+        t0 = time.perf_counter()
+        for _ in range(n_evals):
+            xg = x.clone().requires_grad_(True)
+            coef = coef0.clone().requires_grad_(True)
+            y = O.unet_forward(xg, t_in, ctx, coef, bboxes, locs, p, ocfg)
+            torch.autograd.grad(y, [xg, coef], torch.ones_like(y))
+        t_fb = (time.perf_counter() - t0) / n_evals
+    else:
+        t_fb = 3.0 * t_f
+    e_f = evals_per_image(cfg)
+    e_b = cfg["epochs"] * cfg["steps"] if cfg["optimize"] else 0
+    t_image = e_f * t_f + e_b * max(t_fb - t_f, 0.0)
+    sample = (f"{n_evals} forward and {n_evals} forward+backward UNet evaluation(s) of the CPU oracle (fp32, batch 2, {lat}x{lat} "
+              f"latent, {n_obj} objects): {t_f:.2f} s and {t_fb:.2f} s each"
+              + ("" if bwd_timed else " (backward NOT timed at this size: taken as 2 x forward)")
+              + f"; one image EXTRAPOLATED as {e_f} t_fwd + {e_b} (t_fwd+bwd - t_fwd), no per-block recompute, no VAE decode / "
+              "CLIP loss (the reference has no working CPU backward; this is the oracle port's autograd)")
+    return {"value": 1.0 / t_image, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "extrapolated": True,
+            "evals_timed": 2 * n_evals, "t_fwd_s": t_f, "t_fwd_bwd_s": t_fb}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = 1  # one forward + one forward/backward UNet evaluation per "step" (bounded sample of an image's 153 + 150)
-    n = min(max(1, args.steps), 6) * per_step  # bounded: ~8 s per step on 16 host cores, the run must end within minutes
-    ips, t_f, t_fb, cores = cpu_oracle_images_per_sec(n)
-    sample = _cpu_sample_text(n, t_f, t_fb)
+    cfg = args.cfg
+    n = min(max(1, args.steps), 6)  # bounded: ~8 s per step on 16 host cores, the run must end within minutes
+    cb = cpu_oracle_images_per_sec(n, cfg)
+    ips = cb["value"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": cfg["metric"], "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: SD-v1-4 architecture 512x512, %d PLMS steps, 2-3 objects, "
-                               "alpha inner-opt on (%d epochs), batch=1 per GPU" % (args.ddim_steps, args.epochs)},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "extrapolated": True,
+        "config": {"workload": cfg["workload"]},
+        "cpu_baseline": cb,
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_on_b200": reference_on_b200_record(),
     }
     print(json.dumps(line), flush=True)
 
 
+def reference_on_b200_record():
+    """The UNMODIFIED reference run on a B200 under torch.autocast('cuda') (tools/ref_on_gpu.py, recorded in profiles/): the
+    like-for-like PyTorch yardstick (SURVEY.md §0 'the bar').  A recorded measurement, not re-run here (baseline/_ref is
+    untracked)."""
+    f = ROOT / "profiles" / "r2_reference_on_b200.json"
+    if not f.exists():
+        return None
+    d = json.loads(f.read_text())
+    t = d["timing"]["as_shipped"]
+    return {"images_per_s": t["images_per_s"], "t_fwd_s": t["t_fwd_s"], "t_fwd_bwd_s": t["t_fwd_bwd_s"], "extrapolated": True,
+            "what": d["what"], "gpu": d["gpu"], "when": d["when"], "source": "profiles/r2_reference_on_b200.json"}
+
+
 # ------------------------------------------------------------------------------------------------------
+def build_items(cfg, n_batches, rank, world):
+    """`n_batches` batches of cfg['batch'] work items for this rank (prompts sharded round-robin over the ranks)."""
+    from diffusion_spacetime_attn_b200 import prompts as P
+    from diffusion_spacetime_attn_b200.pipeline import shard_prompts
+
+    records = P.read_gpt(P.SYNTHETIC_GPT)
+    if cfg.get("first_prompt_only"):
+        records = records[:1]
+    need = n_batches * cfg["batch"] * world
+    while len(records) < need:
+        records = records + records
+    records = records[:need]
+    if cfg["objects"] is None:
+        items = P.build_work_items(records)
+    else:
+        pattern = cfg["objects"]
+        items = []
+        for i, rec in enumerate(records):
+            # batches must be homogeneous in object count: the pattern advances per batch, not per item
+            k = pattern[(i // (cfg["batch"] * world)) % len(pattern)]
+            items += P.build_work_items([rec], start=i, force_objects=k)
+    mine = [items[i] for i in shard_prompts(len(items), rank, world)]
+    B = cfg["batch"]
+    return [mine[j * B:(j + 1) * B] for j in range(n_batches)]
+
+
 def run_native(args):
+    t_start = time.perf_counter()
     import torch
     import torch.distributed as dist
 
-    from diffusion_spacetime_attn_b200 import native, ops, prompts as P
-    from diffusion_spacetime_attn_b200.pipeline import SpaceTimeAttnPipeline, broadcast_weights, shard_prompts
+    from diffusion_spacetime_attn_b200 import native, ops
+    from diffusion_spacetime_attn_b200.pipeline import SpaceTimeAttnPipeline, broadcast_weights
 
+    cfg = args.cfg
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -287,18 +380,25 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     native.load()
 
-    pipe = SpaceTimeAttnPipeline(device=f"cuda:{local_rank}", seed=0, steps=args.ddim_steps, num_epochs=args.epochs,
-                                 use_checkpoint=True, checkpoint_min_tokens=args.checkpoint_min_tokens,
-                                 save_images=False, cuda_graphs=not args.eager, half_weights=not args.eager)
+    pipe = SpaceTimeAttnPipeline(device=f"cuda:{local_rank}", seed=0, steps=cfg["steps"], num_epochs=cfg["epochs"],
+                                 latent_size=cfg["latent"], sampler=cfg["sampler"], use_checkpoint=True,
+                                 checkpoint_min_tokens=args.checkpoint_min_tokens, save_images=False,
+                                 cuda_graphs=not args.eager, half_weights=not args.eager)
     bcast_bytes = broadcast_weights(pipe.model) + (broadcast_weights(pipe.clip_loss) if world > 1 else 0)
+    t_built = time.perf_counter()
 
-    total_images = args.warmup + 2 * args.steps
-    records = P.read_gpt(P.SYNTHETIC_GPT)
-    while len(records) < total_images * world:
-        records = records + records
-    items = P.build_work_items(records)
-    mine = [items[i] for i in shard_prompts(len(items), rank, world)][:total_images]
-    conds = [pipe.encode([it]) for it in mine]  # pinned host tensors
+    # warm-up batches first cover every (batch, n_obj) signature of the timed batches (one CUDA-graph capture each)
+    n_sig = len(set(cfg["objects"])) if cfg["objects"] else 2
+    n_warm = max(args.warmup, n_sig)
+    batches = build_items(cfg, n_warm + 2 * args.steps, rank, world)
+    timed = batches[n_warm:]
+    sigs = {len(b[0].object_names) for b in timed}
+    warm = []
+    for sig in sorted(sigs):
+        warm.append(next(b for b in batches if len(b[0].object_names) == sig))
+    warm += [b for b in batches[:n_warm] if b not in warm][:max(0, n_warm - len(warm))]
+    conds = {id(b): pipe.encode(b) for b in batches}  # pinned host tensors
+    opt = cfg["optimize"]
 
     def barrier():
         if world > 1:
@@ -306,14 +406,15 @@ def run_native(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also primes autocast weight caches, cuDNN heuristics, the kernels' smem attributes) ----
-    for i in range(args.warmup):
-        pipe.generate([mine[i]], conds[i], to_host=False)
+    for b in warm:
+        pipe.generate(b, conds[id(b)], optimize_alpha=opt, to_host=False)
     barrier()
+    t_warm = time.perf_counter()
 
     sampler = ClockSampler(local_rank)
     # ---- timed region 1: inputs resident in HBM ----
-    idx = list(range(args.warmup, args.warmup + args.steps))
-    dev_conds = [pipe.to_device(conds[i]) for i in idx]
+    run1, run2 = timed[:args.steps], timed[args.steps:2 * args.steps]
+    dev_conds = [pipe.to_device(conds[id(b)]) for b in run1]
     torch.cuda.reset_peak_memory_stats()
     barrier()
     launches0 = ops.launch_count()
@@ -325,8 +426,8 @@ def run_native(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i, dc in zip(idx, dev_conds):
-        pipe.generate([mine[i]], dc, to_host=False)
+    for b, dc in zip(run1, dev_conds):
+        pipe.generate(b, dc, optimize_alpha=opt, to_host=False, check_device_error=False)
     ev1.record()
     barrier()
     clocks = sampler.stop()
@@ -338,19 +439,18 @@ def run_native(args):
     reserved_mem = torch.cuda.memory_reserved() / 2 ** 30  # includes the graphs' private pools (activation slots)
 
     # ---- timed region 2: end to end through the public API with host buffers ----
-    idx2 = list(range(args.warmup + args.steps, args.warmup + 2 * args.steps))
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     d2h = 0
-    for i in idx2:
-        img = pipe.generate([mine[i]], conds[i], to_host=True)  # H2D of the step's inputs + D2H of the image inside
+    for b in run2:
+        img = pipe.generate(b, conds[id(b)], optimize_alpha=opt, to_host=True)  # H2D of the inputs + D2H of the image inside
         d2h = img.numel() * img.element_size()
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
-    h2d = pipe.h2d_bytes(conds[idx2[0]])
+    h2d = pipe.h2d_bytes(conds[id(run2[0])])
 
     times = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -380,40 +480,59 @@ def run_native(args):
                             "gbs": launch_bytes(kind, key) / (tot / n) / 1e6, "timing": "events in step"})
     kernels.sort(key=lambda r: -r["total_ms"])
     peaks = measured_peaks()
-    traffic = None
-    tf = ROOT / "profiles" / "roofline_traffic.json"
-    roofline = roofline_xattn = None
-    if kernels:
-        top = kernels[0]
-        if tf.exists():
-            traffic = json.loads(tf.read_text()).get(top["kernel"] + ":" + "x".join(map(str, top["geometry"])))
-        attn = [k for k in kernels if "attn" in k["kernel"]]
-        top = attn[0] if attn else kernels[0]  # the dominant ATTENTION kernel (the GroupNorm kernels are HBM streams)
-        roofline = {"kernel": top["kernel"], "geometry": top["geometry"], "bound": "tensor", "achieved": top["tflops"],
-                    "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tflops"],
-                    "traffic": traffic, "peak_source": peaks["source"], "launches": top["launches"],
-                    "mean_launch_us": top["mean_us"], "share_of_step": top["total_ms"] / dev_ms,
-                    "flops_convention": "algorithmic, no recompute (SURVEY.md 8d); sattn_bwd = 2.0 x fwd"}
-        # the fused dual cross-attention (north_star's named kernel) is HBM/latency-bound (38.5*(2+n) FLOP/B): reported
-        # against the measured copy bandwidth, with its tensor throughput next to it
-        xa = [k for k in kernels if k["kernel"] == "sta_xattn_fwd"]
-        if xa:
-            x0 = xa[0]
-            tr = json.loads(tf.read_text()).get("sta_xattn_fwd:" + "x".join(map(str, x0["geometry"]))) if tf.exists() else None
-            roofline_xattn = {"kernel": x0["kernel"], "geometry": x0["geometry"], "bound": "hbm", "achieved": x0["gbs"],
-                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": x0["gbs"] / peaks["hbm_gbs"], "traffic": tr,
-                              "mean_launch_us": x0["mean_us"], "tflops": x0["tflops"],
-                              "note": "algorithmic bytes: q + out + projected contexts + masks (SURVEY.md 8d)"}
+    standalone = bool(hist_graph)
+    tfile = ROOT / "profiles" / "roofline_traffic.json"
+    traffic_db = json.loads(tfile.read_text()) if tfile.exists() else {}
+    how = ("10 launches captured in one CUDA graph between two CUDA events on the launching stream, L2 flushed before "
+           "(includes the inter-node launch gap)" if standalone else "CUDA events around every launch inside the step")
+
+    def top(name):
+        """Dominant geometry of a kernel: the (batch, tokens, heads, head dim) group with the largest total time; within it the
+        object count that has an ncu DRAM-traffic capture on record (n_obj = 2), else the one with the largest time."""
+        rows = [k for k in kernels if k["kernel"] == name]
+        if not rows:
+            return None
+        groups = {}
+        for k in rows:
+            groups.setdefault(tuple(k["geometry"][:4]), []).append(k)
+        best = max(groups.values(), key=lambda g: sum(k["total_ms"] for k in g))
+        with_traffic = [k for k in best if (k["kernel"] + ":" + "x".join(map(str, k["geometry"]))) in traffic_db]
+        return (with_traffic or best)[0]
+
+    def hbm_roofline(k):
+        """The fused dual cross-attention: 38.5 (2 + n_obj) FLOP/B -> HBM/latency-bound."""
+        if k is None:
+            return None
+        return {"kernel": k["kernel"], "geometry": k["geometry"], "bound": "hbm", "achieved": k["gbs"], "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": k["gbs"] / peaks["hbm_gbs"],
+                "traffic": traffic_db.get(k["kernel"] + ":" + "x".join(map(str, k["geometry"]))),
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)" if "measured" in peaks["source"] else peaks["source"],
+                "algorithmic_bytes": launch_bytes(k["kernel"][4:], tuple(k["geometry"])), "launches": k["launches"],
+                "mean_launch_us": k["mean_us"], "tflops": k["tflops"], "share_of_step": k["total_ms"] / dev_ms, "timing": how,
+                "bytes_convention": "q + out (+ d_out, d_q in backward) + projected contexts + masks (SURVEY.md 8d)"}
+
+    def tensor_roofline(k):
+        if k is None:
+            return None
+        # a kernel timed alone is compared with the BURST cuBLAS figure, one timed inside the long step with the sustained one
+        peak = peaks["burst_tflops"] if standalone else peaks["tflops"]
+        return {"kernel": k["kernel"], "geometry": k["geometry"], "bound": "tensor", "achieved": k["tflops"], "peak": peak,
+                "unit": "TFLOP/s", "frac": k["tflops"] / peak,
+                "traffic": traffic_db.get(k["kernel"] + ":" + "x".join(map(str, k["geometry"]))),
+                "peak_source": peaks["source"] + (": bf16_tflops (burst, kernel timed alone)" if standalone else
+                                                  ": bf16_tflops_sustained (kernel timed inside the step)"),
+                "launches": k["launches"], "mean_launch_us": k["mean_us"], "share_of_step": k["total_ms"] / dev_ms, "timing": how,
+                "flops_convention": "algorithmic, no recompute (SURVEY.md 8d); sattn_bwd = 2.0 x fwd"}
 
     if rank == 0:
-        n_img = args.steps * world
+        n_img = args.steps * world * cfg["batch"]
         line = {
-            "metric": METRIC, "value": n_img / (dev_ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": cfg["metric"], "value": n_img / (dev_ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: SD-v1-4 architecture 512x512, %d PLMS steps, 2-3 objects, "
-                                   "alpha inner-opt on (%d epochs), batch=1 per GPU" % (args.ddim_steps, args.epochs),
+            "config": {"workload": cfg["workload"],
                        "weights": pipe.weights, "prompts": "synthetic_gpt.txt (gpt.txt record format)",
+                       "images_per_step": cfg["batch"],
                        "l2": "inputs larger than L2: each step streams ~3.4 GB of weights 300+ times",
                        "execution": ("CUDA graphs per UNet evaluation, fp16 weights; differentiable evaluations keep their "
                                      "activations in HBM slots (fwd-with-grad graph + bwd graph per slot), recompute graph "
@@ -424,17 +543,21 @@ def run_native(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": roofline,
-            "roofline_xattn": roofline_xattn,
-            "kernels": kernels[:12],
+            # headline roofline object: the fused dual cross-attention forward (the kernel BASELINE.json's metric names)
+            "roofline": hbm_roofline(top("sta_xattn_fwd")),
+            "roofline_xattn_bwd": hbm_roofline(top("sta_xattn_bwd")),
+            "roofline_sattn": tensor_roofline(top("sta_sattn_fwd")),
+            "roofline_sattn_bwd": tensor_roofline(top("sta_sattn_bwd")),
+            "kernels": kernels[:14],
             "peak_mem_gib": peak_mem,
             "reserved_mem_gib": reserved_mem,
             "device_error": err,
+            "startup_s": {"build_and_broadcast": t_built - t_start, "capture_and_warmup": t_warm - t_built,
+                          "total_before_timed_region": t_warm - t_start, "warmup_batches": len(warm)},
+            "reference_on_b200": reference_on_b200_record(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            ips, t_f, t_fb, cores = cpu_oracle_images_per_sec(1)
-            line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": _cpu_sample_text(1, t_f, t_fb)}
+            line["cpu_baseline"] = cpu_oracle_images_per_sec(1, cfg)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

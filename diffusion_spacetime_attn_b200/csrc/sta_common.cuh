@@ -92,8 +92,11 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 
 // Bounded wait.  `dead` is a CTA-shared flag: once any wait in the CTA timed out every later wait returns
 // immediately so that the CTA drains to its teardown in microseconds instead of seconds.
+// ~2 s at 1.9 GHz: long enough that time-slicing / preemption of the context (GPU sharing, a debugger) cannot trip it
+// on a healthy kernel — clock64 keeps running while a CTA is descheduled — and short enough that a protocol bug ends a
+// launch in seconds.  Callers read the error word at their sync points (pipeline.generate, tests, bench).
 #ifndef STA_WAIT_TIMEOUT_CYCLES
-#define STA_WAIT_TIMEOUT_CYCLES 400000000ll  // ~0.2 s at 1.9 GHz
+#define STA_WAIT_TIMEOUT_CYCLES 4000000000ll
 #endif
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* dead, unsigned int* err,
                                           unsigned int id) {

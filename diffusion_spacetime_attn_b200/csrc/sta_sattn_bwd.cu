@@ -83,6 +83,14 @@ struct SattnBwdParams {
 // cycle counters of CTA (0,0,0) when STA_DEBUG_FLAGS & 8: [0..4] math warp 2: wait sdp, compute, wait dq, drain, total;
 // [8..10] MMA thread: wait pds, issue, total
 __device__ long long g_bwd_dbg[16];
+// Ablation / cycle-counter paths (skip dQ accumulation, skip dS stores, identity instead of exp2, counters) exist only in
+// a library built with -DSTA_BWD_DEBUG (tools/bwd_cycles.py); in the product they are compiled out: no environment
+// variable can change the gradients, and the branches cost no registers.
+#ifdef STA_BWD_DEBUG
+#define STA_BWD_DBG (p.dbg)
+#else
+#define STA_BWD_DBG 0
+#endif
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -197,7 +205,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         issue_sdp(0, 0);
         issue_sdp(0, 1);
       }
-      const bool prof = (p.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      const bool prof = (STA_BWD_DBG & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       long long m_wait = 0, m_wait_q = 0, m_all = clock64(), mt;
       for (int it = 0; it < total && ok; ++it) {
         const int st = it % ST, pass = it / T, i = it % T;
@@ -291,7 +299,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         fence_proxy_async_smem();
         named_bar_sync(5 + NWG + g, 128);
-        if (t128 == 0 && !(p.dbg & 1)) {
+        if (t128 == 0 && !(STA_BWD_DBG & 1)) {
           tma_reduce_add_4d(g == 0 ? &tm_dq : &tm_dq1, stage, cbase, h, q0row, b);  // OOB rows are clipped by TMA
           bulk_commit_group();
         }
@@ -306,7 +314,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         uint32_t o[8];
         tmem_ld8(src + cc, o);
         tmem_ld_wait();
-        if (qrow < n && !(p.dbg & 1)) {
+        if (qrow < n && !(STA_BWD_DBG & 1)) {
           red_add_v4(dst + cc, __uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
           red_add_v4(dst + cc + 4, __uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]), __uint_as_float(o[7]));
         }
@@ -322,7 +330,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     };
     float pre_val = load_stat(0);
     bool ok = true;
-    const bool prof = (p.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
+    const bool prof = (STA_BWD_DBG & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
     long long c_wait_sdp = 0, c_comp = 0, c_wait_dq = 0, c_drain = 0, t_all = clock64(), tt;
     for (int it = 0; it < total; ++it) {
       const int pass = it / T, i = it % T;
@@ -367,7 +375,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float x = fmaf(__uint_as_float(s[q + e]), p.scale_log2, nlv[e]);
-            pv[e] = (p.dbg & 4) ? x : fast_exp2(x);
+            pv[e] = (STA_BWD_DBG & 4) ? x : fast_exp2(x);
             dv[e] = pv[e] * fmaf(__uint_as_float(dp[q + e]), p.scale, ndv[e]);  // scale * P * (dP - delta)
           }
           pk[q >> 1] = pack_half2(pv[0], pv[1]);
@@ -387,7 +395,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
         for (int cc = 0; cc < CH / 8; ++cc) {
           uint4 v = make_uint4(dk[4 * cc], dk[4 * cc + 1], dk[4 * cc + 2], dk[4 * cc + 3]);
-          if (!(p.dbg & 2)) *reinterpret_cast<uint4*>(ds_blk + sw128_offset(r, chunk0 + cc)) = v;
+          if (!(STA_BWD_DBG & 2)) *reinterpret_cast<uint4*>(ds_blk + sw128_offset(r, chunk0 + cc)) = v;
         }
       }
       tmem_st_wait();
@@ -551,7 +559,11 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   p.scale = a->scale;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.err = device_error_word();
-  p.dbg = getenv("STA_DEBUG_FLAGS") ? atoi(getenv("STA_DEBUG_FLAGS")) : 0;
+#ifdef STA_BWD_DEBUG
+  p.dbg = getenv("STA_DEBUG_FLAGS") ? atoi(getenv("STA_DEBUG_FLAGS")) : 0;  // tools/bwd_cycles.py builds this variant
+#else
+  p.dbg = 0;
+#endif
   static bool attr_set = false;
   if (!attr_set) {
     STA_CUDA_CHECK(cudaFuncSetAttribute(sattn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));

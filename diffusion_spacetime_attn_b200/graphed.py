@@ -296,6 +296,17 @@ class GraphedModelRunner:
         n_obj = len(local_contexts) if local_contexts is not None else 0
         key = (batch2, n_obj, x_shape[2], x_shape[3])
         unet = self.unet
+        # Captured graphs bake in the addresses of the weights and of the caches derived from them (fused QKV matrices,
+        # fp32 bias sums, the timestep-bias table).  If any parameter was re-allocated or rewritten since the capture
+        # (load_state_dict, broadcast, .to()), the graphs are dropped and re-captured instead of replaying stale memory.
+        fp = tuple((p.data_ptr(), p._version) for p in unet.parameters())
+        if fp != getattr(self, "_weights_fp", None):
+            if self.graphs:
+                import warnings
+
+                warnings.warn("UNet weights changed after CUDA-graph capture: dropping %d captured graph set(s)" % len(self.graphs))
+                self.graphs.clear()
+            self._weights_fp = fp
         unet.set_local_contexts(local_contexts, first_timestep=first_timestep)
         g = self.graphs.get(key)
         fresh = g is None

@@ -120,6 +120,11 @@ class AttnBlock(nn.Module):
                 with torch.no_grad():
                     wq = torch.cat([m.weight.detach().reshape(c, c) for m in (self.q, self.k, self.v)]).to(f16).contiguous()
                     bq = torch.cat([m.bias.detach() for m in (self.q, self.k, self.v)]).to(f16).contiguous()
+                prev = slot.get("qkv")
+                if prev is not None and prev[1].shape == wq.shape and prev[1].device == wq.device:
+                    prev[1].copy_(wq)  # in place: captured CUDA graphs keep valid pointers
+                    prev[2].copy_(bq)
+                    wq, bq = prev[1], prev[2]
                 slot["qkv"] = (key, wq, bq)
             _, wq, bq = slot["qkv"]
             q, k, v = F.linear(t, wq, bq).chunk(3, dim=-1)  # [b, hw, c] views

@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -67,6 +67,17 @@ def build_object_masks(bboxs_curr: Sequence[Sequence[float]], n_tokens: int, dev
         dist2 = (axis - box[1]) ** 2
         out[i] = (dist1.unsqueeze(0) + dist2.unsqueeze(1) < MASK_RADIUS_SQ).reshape(-1).to(torch.uint8)
     return out.to(device)
+
+
+def layout_shape(bboxs_curr) -> Tuple[bool, int]:
+    """(per_prompt, n_obj) of a layout argument: `[n_obj][2]` (one layout shared by the batch, the reference's form) or
+    `[B][n_obj][2]` (one layout per prompt; the inner lists are EMPTY for prompts without objects)."""
+    if not bboxs_curr:
+        return False, 0
+    first = bboxs_curr[0]
+    if isinstance(first, (list, tuple)) and (len(first) == 0 or isinstance(first[0], (list, tuple))):
+        return True, len(first)
+    return False, len(bboxs_curr)
 
 
 class GEGLU(nn.Module):
@@ -130,8 +141,17 @@ def cached_sum(owner: nn.Module, name: str, params, dtype) -> torch.Tensor:
                 t = t + p.detach().to(dtype)
             if t.dim() <= 2:  # conv weights keep their (channels_last) memory format
                 t = t.contiguous()
+            if hit is not None and _same_storage_class(hit[1], t):
+                # a weight changed (load_state_dict, broadcast, .to()): refresh IN PLACE so that CUDA graphs captured
+                # over the old tensor (graphed.py) keep reading valid, current data
+                hit[1].copy_(t)
+                t = hit[1]
         slot[name] = hit = (key, t)
     return hit[1]
+
+
+def _same_storage_class(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return a.shape == b.shape and a.dtype == b.dtype and a.device == b.device
 
 
 def _fused_ok(x: torch.Tensor) -> bool:
@@ -179,7 +199,12 @@ class CrossAttention(nn.Module):
         key = tuple((w.data_ptr(), w._version, w.device) for w in ws)
         if getattr(self, "_wqkv_key", None) != key:
             with torch.no_grad():
-                self._wqkv = torch.cat([w.detach() for w in ws], dim=0).to(torch.float16)
+                w = torch.cat([w.detach() for w in ws], dim=0).to(torch.float16)
+                prev = getattr(self, "_wqkv", None)
+                if prev is not None and _same_storage_class(prev, w):
+                    prev.copy_(w)  # in place: captured CUDA graphs keep a valid pointer (see cached_sum)
+                else:
+                    self._wqkv = w
             self._wqkv_key = key
         return self._wqkv
 
@@ -292,7 +317,7 @@ class BasicTransformerBlock(nn.Module):
         k_ctx, v_ctx = self.attn2.project_contexts(torch.stack(slots, dim=1))  # [B, 2 + n_obj, L, C]
         masks = None
         if n_obj:
-            if isinstance(bboxs_curr[0][0], (list, tuple)):  # per-prompt layouts: [B][n_obj][2]
+            if layout_shape(bboxs_curr)[0]:  # per-prompt layouts: [B][n_obj][2]
                 masks = torch.stack([build_object_masks(bb, n, dev) for bb in bboxs_curr])
             else:
                 masks = build_object_masks(bboxs_curr, n, dev).unsqueeze(0).expand(B, -1, -1).contiguous()
@@ -311,7 +336,7 @@ class BasicTransformerBlock(nn.Module):
     def refresh_cache(self, context, bboxs_curr, batch2):
         """Rebuild, in place, every existing cache of this (B, n_obj) signature (graphed.py calls this per prompt)."""
         B = batch2 // 2
-        n_obj = 0 if not bboxs_curr else (len(bboxs_curr[0]) if isinstance(bboxs_curr[0][0], (list, tuple)) else len(bboxs_curr))
+        n_obj = layout_shape(bboxs_curr)[1]
         for key in list(self._caches.keys()):
             if key[0] == B and key[1] == n_obj:
                 self._fill_cache(key, context, bboxs_curr)
@@ -320,10 +345,7 @@ class BasicTransformerBlock(nn.Module):
     def forward(self, x, context=None, time=None, text_index=None, coef=None, bboxs_curr=None):
         if context is None:
             raise ValueError("BasicTransformerBlock needs the text context (SD-v1 always passes one)")
-        if isinstance(bboxs_curr, (list, tuple)) and len(bboxs_curr) and isinstance(bboxs_curr[0][0], (list, tuple)):
-            n_obj = len(bboxs_curr[0])
-        else:
-            n_obj = len(bboxs_curr) if bboxs_curr is not None else 0
+        n_obj = layout_shape(bboxs_curr)[1]
         if torch.is_tensor(time):
             time = int(time.item())  # unmodified callers pass timesteps[0] (a device scalar): one sync, as upstream
         # The reference rebuilds masks / local contexts when `time == 981` (attention.py:240); here the projected

@@ -278,6 +278,9 @@ class UNetModel(nn.Module):
             for rb in blocks:
                 offs[id(rb)] = off
                 off += rb.out_channels
+            if cache is not None and cache[1].shape == table.shape and cache[1].device == table.device:
+                cache[1].copy_(table)  # in place: CUDA graphs captured over the old table keep a valid pointer
+                table = cache[1]
             cache = (key, table, offs)
             self.__dict__["_xb_cache"] = cache
         return cache[1].index_select(0, timesteps), cache[2]

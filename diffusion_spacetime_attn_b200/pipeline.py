@@ -109,7 +109,14 @@ class SpaceTimeAttnPipeline:
                  latent_size: int = 64, sampler: str = "plms", use_checkpoint: bool = True,
                  checkpoint_min_tokens: int = 0, num_epochs: int = 3, save_images: bool = False,
                  out_dir: str = "result_outputs", with_vae: bool = True, unet_config: Optional[dict] = None,
-                 cuda_graphs: bool = True, half_weights: bool = True):
+                 cuda_graphs: bool = True, half_weights: bool = True, allow_synthetic_conditioning: Optional[bool] = None):
+        """`ckpt` = a reference checkpoint (`state_dict` keys of LatentDiffusion).  With a checkpoint the text stage and the
+        CLIP loss must be real too: `$STA_CLIP_L_PATH` (HF CLIP-L/14 text model + tokenizer directory; the checkpoint's own
+        `cond_stage_model.*` tensors are loaded over it) and `$STA_CLIP_B32_PATH` (OpenAI ViT-B/32 state dict) +
+        `$STA_CLIP_TOKENIZER_PATH` (CLIP BPE tokenizer directory).  If one of them is missing the constructor RAISES unless
+        `allow_synthetic_conditioning=True` — trained UNet weights conditioned on hashed noise and optimised against a
+        random-weight loss give meaningless images.  Without a checkpoint everything is synthetic by construction
+        (`self.data == "synthetic"`)."""
         from . import native
 
         native.load()  # fail loudly before building 4 GB of networks if the CUDA library is missing
@@ -160,9 +167,18 @@ class SpaceTimeAttnPipeline:
             self.model.graph_runner = GraphedModelRunner(unet)
         else:
             unet.set_checkpointing(use_checkpoint, checkpoint_min_tokens)
-        self.text = SyntheticTextEmbedder(device="cpu")
+        self.data = "synthetic" if not ckpt else "checkpoint"
+        self.text = None
+        if ckpt:
+            self.text = self._real_text_stage(sd, allow_synthetic_conditioning)
+        if self.text is None:
+            self.text = SyntheticTextEmbedder(device="cpu")
         self.model.cond_stage_model = self.text
-        self.clip_loss = DCLIPLoss(device=self.device, seed=seed + 1) if with_vae else torch.nn.Identity()
+        self.clip_loss = torch.nn.Identity()
+        if with_vae:
+            self.clip_loss = self._real_clip_loss(allow_synthetic_conditioning) if ckpt else None
+            if self.clip_loss is None:
+                self.clip_loss = DCLIPLoss(device=self.device, seed=seed + 1)
         if half_weights and with_vae:
             # fp16 CLIP weights (fp32 LayerNorms): what autocast computes from fp32 masters, minus ~460 cast launches
             # per loss evaluation.  The text features are cached per prompt in fp32.
@@ -174,6 +190,57 @@ class SpaceTimeAttnPipeline:
         cls = DDIMSampler if sampler == "ddim" else PLMSSampler
         self.sampler = cls(self.model, clip_loss_model=self.clip_loss, num_epochs=num_epochs, save_images=save_images,
                            out_dir=out_dir)
+
+    # -- real conditioning when a checkpoint is given (never a silent fallback) -------------------------------
+    def _synthetic_or_raise(self, what: str, hint: str, allow: Optional[bool]):
+        msg = (f"a checkpoint was given but {what} is not available ({hint}); the images would be conditioned on / "
+               "optimised against synthetic stand-ins")
+        if not allow:
+            raise RuntimeError(msg + " — pass allow_synthetic_conditioning=True (--allow_synthetic_conditioning) to accept that")
+        import warnings
+
+        warnings.warn(msg, stacklevel=3)
+        self.data = "checkpoint + SYNTHETIC conditioning"
+        return None
+
+    def _real_text_stage(self, sd, allow):
+        import os
+
+        from .ldm.modules.encoders.modules import FrozenCLIPEmbedder
+
+        path = os.environ.get("STA_CLIP_L_PATH", "")
+        if not os.path.isdir(path):
+            return self._synthetic_or_raise("the CLIP-L/14 text stage", "set STA_CLIP_L_PATH to a local HF model directory", allow)
+        text = FrozenCLIPEmbedder(path, device="cpu")
+        own = {k[len("cond_stage_model."):]: v for k, v in sd.items() if k.startswith("cond_stage_model.")}
+        if own:  # the checkpoint's own text tower wins over the directory's weights
+            missing, unexpected = text.load_state_dict(own, strict=False)
+            if [k for k in missing if "position_ids" not in k]:
+                raise RuntimeError(f"cond_stage_model.* of the checkpoint does not fit CLIPTextModel: missing {missing[:5]}")
+        return text
+
+    def _real_clip_loss(self, allow):
+        import os
+
+        b32, tok = os.environ.get("STA_CLIP_B32_PATH", ""), os.environ.get("STA_CLIP_TOKENIZER_PATH", os.environ.get("STA_CLIP_L_PATH", ""))
+        if not os.path.isfile(b32) or not os.path.isdir(tok):
+            return self._synthetic_or_raise("the CLIP ViT-B/32 loss", "set STA_CLIP_B32_PATH (OpenAI ViT-B-32 state dict) and "
+                                            "STA_CLIP_TOKENIZER_PATH (CLIP BPE tokenizer directory)", allow)
+        from transformers import CLIPTokenizer
+
+        tokenizer = CLIPTokenizer.from_pretrained(tok)
+
+        def tokenize(texts):  # clip.tokenize: <sot> ids <eot>, context length 77 (padding beyond <eot> is never attended)
+            return tokenizer(list(texts), truncation=True, max_length=77, padding="max_length", return_tensors="pt")["input_ids"]
+
+        loss = DCLIPLoss(device=self.device, seed=0, tokenizer=tokenize)
+        state = torch.load(b32, map_location="cpu")
+        state = state.state_dict() if hasattr(state, "state_dict") else state.get("state_dict", state)
+        missing, _ = loss.model.load_openai_state_dict(state)
+        if missing:
+            raise RuntimeError(f"{b32} does not hold an OpenAI CLIP ViT-B/32 state dict: missing {list(missing)[:5]}")
+        loss.model.to(self.device).eval().requires_grad_(False)
+        return loss
 
     # -- stage 1: text (host) ---------------------------------------------------------------------------
     def encode(self, items: Sequence[WorkItem], pin: bool = True) -> Dict[str, torch.Tensor]:
@@ -204,7 +271,7 @@ class SpaceTimeAttnPipeline:
 
     # -- stage 2: sampling + alpha optimisation (device) ----------------------------------------------
     def generate(self, items: Sequence[WorkItem], cond: Dict[str, torch.Tensor], optimize_alpha: bool = True,
-                 alpha=None, to_host: bool = False):
+                 alpha=None, to_host: bool = False, check_device_error: bool = True):
         """Run the sampler on a batch of work items.  `cond` may live on the host (pinned) or on the device.
         Returns the decoded images [B,3,H,W] in [0,1] (on the host when to_host=True) or, without a VAE, the latents."""
         if cond["c"].device != self.device:
@@ -223,6 +290,15 @@ class SpaceTimeAttnPipeline:
                 alpha=alpha)
         res = self.sampler.last_result
         out = res["image"] if res["image"] is not None else res["latent"]
+        if check_device_error:
+            # every mbarrier wait inside the tcgen05 kernels is bounded; a timeout only sets a device-side word (CUDA-graph
+            # replays have no per-launch return code), so it is read here, once per image (one sync per ~second of work)
+            from . import native
+
+            err = native.device_error()
+            if err:
+                raise RuntimeError(f"sta_b200 kernels reported device error 0x{err:x} (mbarrier wait timed out, id {err & 0xff}) "
+                                   "while generating this image: results are invalid")
         if to_host:
             host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
             host.copy_(out, non_blocking=False)

@@ -58,6 +58,9 @@ def build_parser(default_dataset: str) -> argparse.ArgumentParser:
     p.add_argument("--no_alpha_opt", action="store_true")
     p.add_argument("--eager", action="store_true")
     p.add_argument("--force_objects", type=int, default=None)
+    p.add_argument("--allow_synthetic_conditioning", action="store_true",
+                   help="with --ckpt: accept hashed-noise text embeddings / a random-weight CLIP loss when the real CLIP "
+                        "weights are not installed (STA_CLIP_L_PATH, STA_CLIP_B32_PATH); otherwise that is an error")
     return p
 
 
@@ -98,7 +101,9 @@ def run(kind: str, default_dataset: str, argv=None) -> int:
     pipe = SpaceTimeAttnPipeline(device=f"cuda:{local_rank}", ckpt=ckpt, steps=opt.ddim_steps, scale=opt.scale,
                                  latent_size=opt.H // opt.f, sampler="plms" if opt.plms else "ddim",
                                  save_images=not opt.skip_save, out_dir="result_outputs", cuda_graphs=not opt.eager,
-                                 half_weights=not opt.eager)
+                                 half_weights=not opt.eager, allow_synthetic_conditioning=opt.allow_synthetic_conditioning)
+    if rank == 0:
+        print(f"[txt2img-{kind}] weights: {pipe.weights}; data: {pipe.data}", file=sys.stderr)
     if world > 1:
         broadcast_weights(pipe.model)
         broadcast_weights(pipe.clip_loss)
@@ -119,7 +124,7 @@ def run(kind: str, default_dataset: str, argv=None) -> int:
         dt = time.perf_counter() - t0
         done += 1
         if log:
-            log.write(json.dumps({"prompt_idx": it.prompt_idx, "prompt": it.prompt, "n_obj": len(it.object_names),
+            log.write(json.dumps({"prompt_idx": it.prompt_idx, "prompt": it.prompt, "n_obj": len(it.object_names), "data": pipe.data,
                                   "seconds": dt, "losses": pipe.sampler.last_result["losses"]}) + "\n")
             log.flush()
         print(f"[rank {rank}] prompt {it.prompt_idx}: {dt:.2f} s  ({it.prompt})")

@@ -246,3 +246,30 @@ def test_timestep_bias_table_matches_per_block_projection():
         assert (got - ref).abs().max().item() < 2e-2 * (1 + ref.abs().max().item())
     again, _ = m._timestep_bias(t)
     assert again.data_ptr() != xb.data_ptr() and m.__dict__["_xb_cache"][1].shape[0] == 64  # cached table, fresh gather
+
+
+def test_layout_shape_handles_shared_per_prompt_and_empty_layouts():
+    from diffusion_spacetime_attn_b200.ldm.modules.attention import layout_shape
+
+    assert layout_shape(None) == (False, 0) and layout_shape([]) == (False, 0)
+    assert layout_shape([[0.3, 0.5], [0.7, 0.5]]) == (False, 2)            # the reference's form: one layout, 2 objects
+    assert layout_shape([[[0.3, 0.5]], [[0.7, 0.5]]]) == (True, 1)         # B = 2 prompts, one object each
+    assert layout_shape([[], []]) == (True, 0)                             # B = 2 prompts WITHOUT objects (used to raise)
+    assert layout_shape([(0.3, 0.5)]) == (False, 1)
+
+
+def test_checkpoint_without_real_clip_is_an_error_not_a_silent_fallback(monkeypatch):
+    """with --ckpt the text stage / CLIP loss must be real, or the caller must opt in to synthetic stand-ins."""
+    from diffusion_spacetime_attn_b200.pipeline import SpaceTimeAttnPipeline
+
+    for var in ("STA_CLIP_L_PATH", "STA_CLIP_B32_PATH", "STA_CLIP_TOKENIZER_PATH"):
+        monkeypatch.delenv(var, raising=False)
+    pipe = object.__new__(SpaceTimeAttnPipeline)  # no networks needed for the policy itself
+    pipe.data = "checkpoint"
+    with pytest.raises(RuntimeError, match="allow_synthetic_conditioning"):
+        pipe._real_text_stage({}, None)
+    with pytest.raises(RuntimeError, match="allow_synthetic_conditioning"):
+        pipe._real_clip_loss(False)
+    with pytest.warns(UserWarning, match="synthetic"):
+        assert pipe._real_text_stage({}, True) is None
+    assert "SYNTHETIC" in pipe.data

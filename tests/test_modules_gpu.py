@@ -391,8 +391,38 @@ def test_config2_full_run_graph_execution_matches_eager(loss):
           f"latent rel L2 {e_z:.3e}; dL/dalpha rel L2 per epoch {e_g}; |dL/dalpha| eager {[float(g.norm()) for g in g_e]}; "
           f"losses eager {l_e} graph {l_g}")
     assert upd_e.abs().max().item() > 5e-3, "Adam must have moved the weights (3 steps at lr 5e-3)"
-    assert abs(l_e[0] - l_g[0]) < 5e-3 * abs(l_e[0]) + 1e-3  # epoch 0 starts from identical weights
-    if loss == "linear":
+    if loss == "clip":
+        assert abs(l_e[0] - l_g[0]) < 5e-3 * abs(l_e[0]) + 1e-3  # epoch 0 starts from identical weights
+    if loss == "linear":  # (<z_0, G> itself is a cancelling sum of 16 k terms: compare the latent and the gradient instead)
         assert e_g[0] < 5e-2, f"epoch-0 dL/dalpha: graph vs eager relative L2 {e_g[0]:.3e}"
         assert agree >= 0.9 and dw <= 0.5 * upd_e.abs().max().item() + 1e-4
     assert e_z < 2e-2
+
+
+@pytest.mark.gpu
+def test_two_prompts_without_objects_in_one_call():
+    """B = 2 prompts with ZERO objects each (`bboxs_curr=[[], []]`): the reference supports the no-object case
+    (attention.py:238,277: empty loops); batched it used to raise IndexError here.  Must equal plain
+    classifier-free-guided sampling of each prompt on its own."""
+    m, sd, cfg = _tiny_models(7)
+    ld = LatentDiffusion(unet_config={"params": dict(TINY)}, build_first_stage=False)
+    ld.model.diffusion_model = m
+    ld = ld.cuda().eval().requires_grad_(False)
+    S, lat, B = 4, 16, 2
+    g = torch.Generator().manual_seed(33)
+    x_T = torch.randn(B, 4, lat, lat, generator=g)
+    uc = uncond().expand(B, -1, -1).contiguous()
+    c = torch.cat([ctx_tensor(400), ctx_tensor(401)])
+    sampler = PLMSSampler(ld, clip_loss_model=torch.nn.Identity(), save_images=False)
+    with torch.autocast("cuda"):
+        sampler.sample(S=S, batch_size=B, shape=[4, lat, lat], conditioning=c.cuda(), x_T=x_T.cuda(),
+                       unconditional_guidance_scale=7.5, unconditional_conditioning=uc.cuda(), text_index=0,
+                       curr_text=["p0", "p1"], bboxs_curr=[[], []], seed=1, prompt_idx=[0, 1], object_names=[[], []],
+                       local_conditionings=[], optimize_alpha=True)
+    got = sampler.last_result["latent"].float().cpu()
+    assert native.device_error() == 0
+    sch = O.make_schedule(S)
+    for b in range(B):
+        eps = lambda x, t, i: O.guided_eps(x, t, torch.zeros(0), uc[b:b + 1], c[b:b + 1], [], uncond(), [], sd, cfg)
+        z = O.plms_trajectory(eps, x_T[b:b + 1], S, sch)
+        assert rel_l2(got[b:b + 1], z) < 1e-2, f"prompt {b}"

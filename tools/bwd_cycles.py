@@ -1,4 +1,5 @@
-"""Cycle breakdown of sta_sattn_bwd (CTA 0: one math warp and the MMA-issue thread), STA_DEBUG_FLAGS=8.
+"""Cycle breakdown of sta_sattn_bwd (CTA 0: one math warp and the MMA-issue thread), STA_DEBUG_FLAGS=8, from a separate
+-DSTA_BWD_DEBUG build of the library (the product has these paths compiled out).
 
   STA_DEBUG_FLAGS=8 python tools/bwd_cycles.py [b n h d]
 """
@@ -8,9 +9,26 @@ import sys
 from pathlib import Path
 
 os.environ.setdefault("STA_DEBUG_FLAGS", "8")
+import subprocess  # noqa: E402
+
 import torch  # noqa: E402
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from diffusion_spacetime_attn_b200 import build as B  # noqa: E402
+
+
+def build_debug():
+    """The counters / ablations are compiled out of the product: build csrc/build/libsta_b200_bwddbg.so with -DSTA_BWD_DEBUG."""
+    B.build_native()
+    out, obj = B.BUILD / "libsta_b200_bwddbg.so", B.BUILD / "sta_sattn_bwd_dbg.o"
+    subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DSTA_BWD_DEBUG", "-I", str(B.INCLUDE), "-c", str(B.CSRC / "sta_sattn_bwd.cu"),
+                    "-o", str(obj)], check=True, capture_output=True)
+    objs = [str(B.BUILD / (s.stem + ".o")) for s in sorted(B.CSRC.glob("*.cu")) if s.stem != "sta_sattn_bwd"] + [str(obj)]
+    subprocess.run([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs], check=True)
+    return out
+
+
+os.environ["STA_B200_LIB"] = str(build_debug())
 from diffusion_spacetime_attn_b200 import native, ops  # noqa: E402
 
 b, n, h, d = (int(v) for v in sys.argv[1:5]) if len(sys.argv) >= 5 else (2, 4096, 8, 40)

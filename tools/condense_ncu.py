@@ -1,7 +1,8 @@
 """Condense `ncu --set full --csv --page raw` captures (one kernel each) into metric,unit,value tables for profiles/.
 
-  python tools/condense_ncu.py gpurun_out/r1b/full_*.csv   ->  profiles/r1_ncu_full_<name>.csv
+  python tools/condense_ncu.py gpurun_out/r2_full_*.csv   ->  profiles/r2_ncu_full_<name>.csv   (prefix: $NCU_PREFIX, default r2)
 """
+import os
 import csv
 import re
 import sys
@@ -25,8 +26,8 @@ for f in sys.argv[1:]:
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     names, units, vals = rows[hdr], rows[hdr + 1], rows[hdr + 2]
     kname = vals[names.index("Kernel Name")]
-    tag = Path(f).stem.replace("full_", "")
-    with open(out_dir / f"r1_ncu_full_{tag}.csv", "w") as o:
+    tag = Path(f).stem.replace("r2_full_", "").replace("full_", "")
+    with open(out_dir / f"{os.environ.get('NCU_PREFIX', 'r2')}_ncu_full_{tag}.csv", "w") as o:
         o.write("metric,unit,value\n")
         o.write(f"Kernel Name,,{kname.replace(',', ';')}\n")
         for n, u, v in zip(names, units, vals):
