@@ -49,12 +49,68 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-map cache ("the library allocates nothing persistent except cached CUtensorMaps keyed by
+// (ptr, shape)").  cuTensorMapEncodeTiled costs ~1-2 us of host time per map and the attention launchers build 4-6 maps per
+// call; eager callers hit the same (pointer, geometry) over and over (q/k/v views of the cached-allocator's blocks), CUDA
+// graphs do not care.  A tensor map is a pure function of its encode arguments, so a stale entry cannot exist: the key IS
+// the full argument list.  Small direct-mapped table, one mutex.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct TmapKey {
+  const void* base;
+  int rank, kind;
+  uint64_t dims[5], strides[5];
+  uint32_t box[5];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+  bool used = false;
+  TmapKey key;
+  CUtensorMap map;
+};
+constexpr int kTmapSlots = 1024;
+TmapSlot g_tmap_cache[kTmapSlots];
+std::mutex g_tmap_mu;
+
+TmapKey make_key(const void* base, int rank, int kind, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+  TmapKey k;
+  memset(&k, 0, sizeof(k));  // padding bytes take part in the comparison
+  k.base = base;
+  k.rank = rank;
+  k.kind = kind;
+  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.strides[i] = strides[i]; k.box[i] = box[i]; }
+  return k;
+}
+size_t hash_key(const TmapKey& k) {
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+  uint64_t h = 1469598103934665603ull;  // FNV-1a
+  for (size_t i = 0; i < sizeof(TmapKey); ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return static_cast<size_t>(h % kTmapSlots);
+}
+bool tmap_lookup(const TmapKey& k, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  const TmapSlot& s = g_tmap_cache[hash_key(k)];
+  if (s.used && s.key == k) { *out = s.map; return true; }
+  return false;
+}
+void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lock(g_tmap_mu);
+  TmapSlot& s = g_tmap_cache[hash_key(k)];
+  s.used = true;
+  s.key = k;
+  s.map = m;
+}
+}  // namespace
+
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(STA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
     return fail(STA_ERR_UNSUPPORTED, "tensor base %p is not 16-byte aligned", base);
+  const TmapKey key = make_key(base, rank, /*kind=*/0, dims, strides_bytes, box);
+  if (tmap_lookup(key, out)) return STA_OK;
   cuuint64_t gdim[5], gstr[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
@@ -72,6 +128,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(STA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  tmap_store(key, *out);
   return STA_OK;
 }
 

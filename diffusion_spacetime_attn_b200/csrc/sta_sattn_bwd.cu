@@ -125,10 +125,13 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ __align__(16) float s_lse2_buf[NSB][128], s_delta_buf[NSB][128];
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // head dim 160: the two accumulator column passes ([0,128) and [128,160)) run in DIFFERENT CTAs (grid.x = key tiles x
+  // NPASS): each recomputes S^T / dP^T / P / dS for its key tile, which costs nothing on the idle SMs of these small
+  // layers (N <= 576: 32 CTAs before), and halves the serial chain of a CTA.
+  const int j = blockIdx.x / Cfg::NPASS, pass_cta = blockIdx.x % Cfg::NPASS, h = blockIdx.y, b = blockIdx.z;
   const int n = p.n;
   const int T = (n + 127) / 128;
-  const int total = Cfg::NPASS * T;
+  const int total = T;
 
   if (tid == 0) {
     dead = 0;
@@ -208,7 +211,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const bool prof = (STA_BWD_DBG & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       long long m_wait = 0, m_wait_q = 0, m_all = clock64(), mt;
       for (int it = 0; it < total && ok; ++it) {
-        const int st = it % ST, pass = it / T, i = it % T;
+        const int st = it % ST, pass = pass_cta, i = it;
         const int nacc = (Cfg::NPASS == 1) ? DMMA : (pass == 0 ? 128 : DMMA - 128);
         const uint32_t col_off = pass * 2 * kSBBlockBytes;               // first 64-column block of this pass
         const uint32_t idesc_acc = umma_idesc_f16(128, nacc, 0, 1);      // A K-major (TMEM or smem), B MN-major
@@ -275,8 +278,8 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const float* lse_bh = p.lse + ((long long)b * p.heads + h) * n;
     const float* delta_bh = p.delta + ((long long)b * p.heads + h) * n;
     auto drain_dq = [&](int it_d) {
-      const int q0row = (it_d % T) * 128, col0 = (it_d / T) * 128;
-      const int ncols = (Cfg::NPASS == 1) ? D : (it_d / T == 0 ? 128 : D - 128);
+      const int q0row = it_d * 128, col0 = pass_cta * 128;
+      const int ncols = (Cfg::NPASS == 1) ? D : (pass_cta == 0 ? 128 : D - 128);
       const uint32_t src = lane_addr + Cfg::TMEM_DQ + (it_d & 1) * Cfg::DQ_STRIDE;
       if (Cfg::PIPE_DRAIN) {
         // TMEM -> fp32 smem tile -> ONE TMA reduce-add per warpgroup and tile (the per-thread red.global path below
@@ -333,7 +336,7 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const bool prof = (STA_BWD_DBG & 8) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
     long long c_wait_sdp = 0, c_comp = 0, c_wait_dq = 0, c_drain = 0, t_all = clock64(), tt;
     for (int it = 0; it < total; ++it) {
-      const int pass = it / T, i = it % T;
+      const int pass = pass_cta, i = it;
       const int col0 = pass * 128;                                             // first head-dim column of this pass
       const int ncols = (Cfg::NPASS == 1) ? D : (pass == 0 ? 128 : D - 128);   // columns of this pass
       // stage lse / delta of this warpgroup's 64 query columns for broadcast reads (values were prefetched from
@@ -564,12 +567,12 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
 #else
   p.dbg = 0;
 #endif
-  static bool attr_set = false;
-  if (!attr_set) {
-    STA_CUDA_CHECK(cudaFuncSetAttribute(sattn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL));
-    attr_set = true;
-  }
-  dim3 grid((a->n + 127) / 128, a->heads, a->batch);
+  static PerDeviceOnce smem_attr;
+  if ((rc = smem_attr.run([] {
+        return cudaFuncSetAttribute(sattn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_TOTAL);
+      })))
+    return rc;
+  dim3 grid(((a->n + 127) / 128) * Cfg::NPASS, a->heads, a->batch);
   sattn_bwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_TOTAL, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, tm_dq1, p);
   STA_CUDA_CHECK(cudaGetLastError());
 

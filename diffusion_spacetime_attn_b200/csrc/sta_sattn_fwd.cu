@@ -351,11 +351,11 @@ static int launch_sattn_fwd(const sta_sattn_fwd_args* a, cudaStream_t stream) {
   p.o_batch_stride = a->o_batch_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.err = device_error_word();
-  static bool attr_set = false;
-  if (!attr_set) {
-    STA_CUDA_CHECK(cudaFuncSetAttribute(sattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static PerDeviceOnce smem_attr;
+  int rc_attr = smem_attr.run([] {
+    return cudaFuncSetAttribute(sattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  if (rc_attr) return rc_attr;
   dim3 grid((a->n + 128 * Cfg::NQ - 1) / (128 * Cfg::NQ), a->heads, a->batch);
   sattn_fwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_k, tm_v, p);
   STA_CUDA_CHECK(cudaGetLastError());
