@@ -363,6 +363,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-4 polynomial, relative error < 5e-5: below the fp16 rounding of
+// the probabilities it feeds).  The MUFU pipe retires 16 ex2 per clock per SM and is what bounds the head-dim-40
+// self-attention (XU 71 % busy, FMA 19 %, issue 45 % in ncu): evaluating a fraction of the exponentials here moves that
+// fraction to pipes that idle.  x <= ~8 (lazy-rescaled scores); x = -inf (masked keys) gives ~0.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;  // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);  // [-0.5, 0.5]
+  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));  // * 2^round(x)
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

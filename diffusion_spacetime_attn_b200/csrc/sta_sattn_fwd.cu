@@ -17,6 +17,10 @@
 #include "sta_common.cuh"
 #include "sta_host.h"
 
+#ifndef STA_POLY_EVERY
+#define STA_POLY_EVERY 0  // k > 0: 1 pair in k on the FMA pipe.  Measured on B200 (L0, us): 0: 111.6, 6: 115.7, 4: 117.8, 3: 130.0, 2: 150.7 -> off
+#endif
+
 namespace sta {
 
 constexpr int kBlockBytes = 128 * 128;  // one 64-column block of a 128-row tile
@@ -269,8 +273,12 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 128; c += 2) {  // exp in place: the packed pair (c, c+1) lands in s[c/2]
-          const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2, -m_ref));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -m_ref));
+          // every STA_POLY_EVERY-th pair is evaluated on the FMA pipe instead of the MUFU pipe (see poly_exp2)
+          const bool poly = (STA_POLY_EVERY > 0) && ((c >> 1) % (STA_POLY_EVERY > 0 ? STA_POLY_EVERY : 1) == (STA_POLY_EVERY - 1));
+          const float x0 = fmaf(__uint_as_float(s[c]), p.scale_log2, -m_ref);
+          const float x1 = fmaf(__uint_as_float(s[c + 1]), p.scale_log2, -m_ref);
+          const float p0 = poly ? poly_exp2(x0) : fast_exp2(x0);
+          const float p1 = poly ? poly_exp2(x1) : fast_exp2(x1);
           l0 += p0;
           l1 += p1;
           s[c >> 1] = pack_half2(p0, p1);

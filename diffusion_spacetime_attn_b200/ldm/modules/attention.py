@@ -276,6 +276,7 @@ class BasicTransformerBlock(nn.Module):
                 self.uncond = torch.load(path, map_location="cpu")
             except Exception:  # noqa: BLE001 - the shipped file is pickled on cuda:0
                 self.uncond = None
+        self.defer_ff_bias = False  # set by SpatialTransformer._forward_fused for its last block (see _forward_fused)
         self.first_timestep = 981  # reference hard-codes 981 (attention.py:240); samplers overwrite per schedule
         self.local_contexts: Optional[List[torch.Tensor]] = None  # in-memory c_i [B, 77, ctx_dim] (or [1, ...])
         self._cache = None
@@ -365,8 +366,11 @@ class BasicTransformerBlock(nn.Module):
     def _dropout_free(self) -> bool:
         return not self.training or all(m.p == 0.0 for m in self.modules() if isinstance(m, nn.Dropout))
 
+    def _use_fused(self, x) -> bool:
+        return _fused_ok(x) and isinstance(self.ff.net[0], GEGLU) and self._dropout_free() and _frozen(self)
+
     def _forward(self, x, context=None, coef=None, bboxs_curr_input=None):
-        if _fused_ok(x) and isinstance(self.ff.net[0], GEGLU) and self._dropout_free() and _frozen(self):
+        if self._use_fused(x):
             return self._forward_fused(x, coef)
         return self._forward_unfused(x, coef)
 
@@ -410,6 +414,10 @@ class BasicTransformerBlock(nn.Module):
             proj, out = ff.net[0].proj, ff.net[2]
             pb = proj.bias if proj.bias.dtype == torch.float16 else cached_sum(self, "pb", [proj.bias], torch.float16)
             gated = ops.geglu(F.linear(n3, w16(proj), pb))
+            if self.defer_ff_bias:
+                # last block of a SpatialTransformer: the residual rides in the GEMM (D = gated W^T + x2, fp32 accumulate) and
+                # the bias is folded into proj_out's bias by the caller (proj_out is affine) — one launch fewer per block
+                return torch.addmm(x2.reshape(-1, x2.shape[-1]), gated.reshape(-1, gated.shape[-1]), w16(out).t()).view_as(x2)
             t = F.linear(gated, w16(out))
             return ops.bias_residual_add(t, cached_sum(self, "bo3", [out.bias], f32), x2)
 
@@ -460,12 +468,31 @@ class SpatialTransformer(nn.Module):
         w_out = cached_sum(self, "w_out", [self.proj_out.weight], torch.float16).reshape(c, -1)
         with torch.autocast("cuda", enabled=False):
             t = F.linear(xn, w_in, cached_sum(self, "b_in", [self.proj_in.bias], torch.float16))
+        last = self.transformer_blocks[-1]
+        defer = last._use_fused(t)
         for block in self.transformer_blocks:
+            block.defer_ff_bias = defer and block is last
             t = block(t, context=context, time=time, text_index=text_index, coef=coef, bboxs_curr=bboxs_curr)
+        b_out = self._deferred_out_bias(last, w_out) if defer else cached_sum(self, "b_out", [self.proj_out.bias], f32)
         with torch.autocast("cuda", enabled=False):
             t = F.linear(_fp16(t), w_out)
-            out = ops.bias_residual_add(t, cached_sum(self, "b_out", [self.proj_out.bias], f32), x_in)
+            out = ops.bias_residual_add(t, b_out, x_in)
         return tokens_nhwc(out, h, w)
+
+    @torch.no_grad()
+    def _deferred_out_bias(self, last, w_out) -> torch.Tensor:
+        """proj_out.bias + W_out @ b_ff: the last block left out its FeedForward output bias b_ff (defer_ff_bias) and
+        proj_out(y + b_ff) = proj_out(y) + W_out b_ff.  fp32, cached, refreshed in place when a weight changes."""
+        params = (self.proj_out.bias, self.proj_out.weight, last.ff.net[2].bias)
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        hit = self.__dict__.get("_sta_defer_bias")
+        if hit is None or hit[0] != key:
+            t = self.proj_out.bias.float() + w_out.float() @ last.ff.net[2].bias.float()
+            if hit is not None and hit[1].shape == t.shape and hit[1].device == t.device:
+                hit[1].copy_(t)
+                t = hit[1]
+            self.__dict__["_sta_defer_bias"] = hit = (key, t)
+        return hit[1]
 
     def forward(self, x, context=None, time=None, text_index=None, coef=None, bboxs_curr=None):
         b, c, h, w = x.shape
@@ -481,6 +508,7 @@ class SpatialTransformer(nn.Module):
         x = self.proj_in(x)
         x = x.permute(0, 2, 3, 1).reshape(b, h * w, -1)  # 'b c h w -> b (h w) c'
         for block in self.transformer_blocks:
+            block.defer_ff_bias = False
             x = block(x, context=context, time=time, text_index=text_index, coef=coef, bboxs_curr=bboxs_curr)
         x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)  # 'b (h w) c -> b c h w'
         x = self.proj_out(x)

@@ -39,6 +39,23 @@ def gn_silu(norm: nn.GroupNorm, x, silu: bool = True):
     return _ops.group_norm_silu(x, w, b, norm.eps, silu)
 
 
+class _TimeEmbedding:
+    """Stands in for the timestep embedding `emb` when UNetModel's per-timestep table already holds what every ResBlock
+    needs from it (`_sta_xb`); `value()` evaluates the time_embed MLP on first use, for blocks that take the plain path."""
+
+    def __init__(self, compute):
+        self._compute, self._value = compute, None
+
+    def value(self):
+        if self._value is None:
+            self._value = self._compute()
+        return self._value
+
+
+def _emb_tensor(emb):
+    return emb.value() if isinstance(emb, _TimeEmbedding) else emb
+
+
 class TimestepBlock(nn.Module):
     """Marker: forward(x, emb)."""
 
@@ -132,6 +149,7 @@ class ResBlock(TimestepBlock):
                 off = slot[1][id(self)]
                 xb = slot[0][:, off:off + self.out_channels]
             else:
+                emb = _emb_tensor(emb)
                 act = getattr(emb, "_sta_silu", None)  # SiLU(emb) is shared by all ResBlocks
                 if act is None:
                     act = F.silu(emb)
@@ -161,7 +179,7 @@ class ResBlock(TimestepBlock):
             return self._forward_fused(x, emb)
         fused = _fusable(x)
         h = self.in_layers[2](gn_silu(self.in_layers[0], x)) if fused else self.in_layers(x)
-        emb_out = self.emb_layers(emb).type(h.dtype)
+        emb_out = self.emb_layers(_emb_tensor(emb)).type(h.dtype)
         h = h + emb_out[:, :, None, None]
         if fused and _fusable(h):
             h = self.out_layers[3](self.out_layers[2](gn_silu(self.out_layers[0], h)))  # [2] = Dropout(p)
@@ -306,11 +324,17 @@ class UNetModel(nn.Module):
         """x [2B,4,H,W], timesteps [2B], context [2B,77,768] -> eps [2B,4,H,W]   (reference :710-742)."""
         assert y is None, "SD-v1 is not class-conditional"
         hs = []
-        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels, repeat_only=False))
-        if not emb.requires_grad:
-            if emb.is_cuda and timesteps.is_cuda and timesteps.dtype == th.long and _frozen(self):
-                emb._sta_xb = self._timestep_bias(timesteps)
-            else:
+        def compute_emb():
+            return self.time_embed(timestep_embedding(timesteps, self.model_channels, repeat_only=False))
+
+        if x.is_cuda and timesteps.is_cuda and timesteps.dtype == th.long and _frozen(self):
+            # every ResBlock's projected embedding comes out of the per-timestep table: the time_embed MLP itself (sin / cos /
+            # cat / two Linear + SiLU = 13 launches per evaluation) only runs if some block asks for the raw embedding
+            emb = _TimeEmbedding(compute_emb)
+            emb._sta_xb = self._timestep_bias(timesteps)
+        else:
+            emb = compute_emb()
+            if not emb.requires_grad:
                 emb._sta_silu = F.silu(emb)  # every ResBlock starts its embedding branch with the same SiLU (:217-223)
         # the reference hands timesteps[0] (a device scalar) to every block, which then syncs on `time == 981`
         # (attention.py:240); callers of this package pass the same value as a host int instead
