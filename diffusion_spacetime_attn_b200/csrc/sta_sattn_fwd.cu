@@ -52,6 +52,7 @@ struct SattnFwdParams {
   long long o_token_stride, o_batch_stride;
   float scale_log2;  // scale * log2(e)
   unsigned int* err;
+  int q_per_cta;  // query tiles handled by one CTA: NQ, or 1 when NQ tiles per CTA would leave SMs idle (small layers)
 };
 
 template <int D>
@@ -74,10 +75,11 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ int dead;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  const int q0 = blockIdx.x * (128 * NQ), h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (128 * p.q_per_cta), h = blockIdx.y, b = blockIdx.z;
   const int n = p.n;
   const int T = (n + 127) / 128;                           // KV tiles
-  const int nq_active = (NQ == 2 && q0 + 128 < n) ? 2 : 1;  // second query tile may be past the end
+  // second query tile: only with two tiles per CTA, and it may be past the end of the sequence
+  const int nq_active = (NQ == 2 && p.q_per_cta == 2 && q0 + 128 < n) ? 2 : 1;
 
   if (tid == 0) {
     dead = 0;
@@ -364,7 +366,19 @@ static int launch_sattn_fwd(const sta_sattn_fwd_args* a, cudaStream_t stream) {
     return cudaFuncSetAttribute(sattn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   if (rc_attr) return rc_attr;
-  dim3 grid((a->n + 128 * Cfg::NQ - 1) / (128 * Cfg::NQ), a->heads, a->batch);
+  // Two query tiles per CTA (two softmax warpgroups ping-ponging on one tensor pipe) is the efficient shape when the grid
+  // fills the GPU; on the small layers (N = 1024: 64 CTAs) one tile per CTA doubles the number of busy SMs instead.
+  static std::atomic<int> sm_count{0};  // every GPU of a box has the same SM count: one query per process
+  int num_sms = sm_count.load(std::memory_order_relaxed);
+  if (num_sms == 0) {
+    int dev = 0;
+    num_sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    sm_count.store(num_sms, std::memory_order_relaxed);
+  }
+  const long long ctas_nq = (long long)((a->n + 128 * Cfg::NQ - 1) / (128 * Cfg::NQ)) * a->heads * a->batch;
+  p.q_per_cta = (Cfg::NQ == 2 && ctas_nq < num_sms) ? 1 : Cfg::NQ;
+  dim3 grid((a->n + 128 * p.q_per_cta - 1) / (128 * p.q_per_cta), a->heads, a->batch);
   sattn_fwd_kernel<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_q, tm_k, tm_v, p);
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;

@@ -54,6 +54,6 @@ print(f"sattn_bwd {b}x{n}x{h}x{d}: {a.elapsed_time(e) / 10 * 1e3:.1f} us per cal
 names = ["math: wait S/dP", "math: P/dS compute", "math: wait dQ", "math: drain dQ", "math: total"]
 for nm, val in zip(names, vals[:5]):
     print(f"  {nm:22s} {val:9d} cycles  {val / max(tiles, 1):8.0f} per tile")
-for nm, val in zip(["mma: wait P/dS", "mma: issue", "mma: total"], vals[8:11]):
+for nm, val in zip(["mma: wait P/dS", "mma: wait Q/dO", "mma: total"], vals[8:11]):
     print(f"  {nm:22s} {val:9d} cycles  {val / max(tiles, 1):8.0f} per tile")
 print("device_error", native.device_error())
