@@ -138,3 +138,32 @@ def test_xattn_bwd_matches_oracle_autograd(shape):
     if n_obj:
         rel = (d_coef.cpu() - cf.grad).abs() / (cf.grad.abs() + 1e-2 * cf.grad.abs().max() + 1e-6)
         assert rel.max().item() < 2e-2, f"d_coef rel err {rel.max().item():.3e}: {d_coef.cpu()} vs {cf.grad}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ctx_len", [80, 64, 17, 1])
+@pytest.mark.parametrize("d", [40, 160])
+def test_xattn_context_lengths_other_than_77(ctx_len, d):
+    """The C ABI takes any ctx_len in [1, 80] (CLIP's 77 is only the common case): the padding columns of the 80-wide score
+    tiles must be masked in the forward softmax and in the backward's recomputed P for every length."""
+    B, n, h, n_obj = 1, 300, 2, 2
+    g = torch.Generator().manual_seed(100 + ctx_len + d)
+    C = h * d
+    q = torch.randn(2 * B, n, C, generator=g).half()
+    k = torch.randn(B, 2 + n_obj, ctx_len, C, generator=g).half()
+    v = torch.randn(B, 2 + n_obj, ctx_len, C, generator=g).half()
+    masks = (torch.rand(B, n_obj, n, generator=g) < 0.4).to(torch.uint8)
+    coef = (torch.rand(B, n_obj, generator=g) * 3 + 0.5).float()
+    d_out = (torch.randn(2 * B, n, C, generator=g) * 0.1).half()
+    qf, cf = q.float().requires_grad_(True), coef.clone().requires_grad_(True)
+    ref = O.dual_cross_attention_core(qf, k.float(), v.float(), masks, cf, h)
+    (ref * d_out.float()).sum().backward()
+    dev = lambda t: t.cuda()
+    out, lse = ops.xattn_fwd(dev(q), dev(k), dev(v), dev(masks), dev(coef), h)
+    d_q, d_coef = ops.xattn_bwd(dev(q), dev(k), dev(v), dev(masks), dev(coef), lse, dev(d_out), h, out=out)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    _close(out, ref.detach())
+    _close(d_q, qf.grad, atol=3e-3, rtol=2e-2)
+    rel = (d_coef.cpu() - cf.grad).abs() / (cf.grad.abs() + 1e-2 * cf.grad.abs().max() + 1e-6)
+    assert rel.max().item() < 2e-2
