@@ -26,6 +26,24 @@ from ...modules.diffusionmodules.util import make_ddim_sampling_parameters, make
 
 mode = "fix_radius_0p2"
 
+# NVTX ranges (prompt / epoch / step / decode+loss / backward) for nsys / ncu --nvtx timelines: STA_NVTX=1.  Off by default:
+# a range push/pop per step is host work inside the sampling loop.
+_NVTX = os.environ.get("STA_NVTX", "0") == "1"
+
+
+class _nvtx_range:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 def _per_prompt(value, B):
     """bboxs / names may be given once (shared by all prompts) or per prompt."""
@@ -103,9 +121,10 @@ class PLMSSampler(object):
             index = total - i - 1
             t_next = int(time_range[min(i + 1, total - 1)])
             coef = W[:, :, i] if W is not None else None
-            img, _, e_t = self.p_sample_plms(img, cond, int(step), index=index, unconditional_guidance_scale=scale,
-                                             unconditional_conditioning=uc, old_eps=old_eps, t_next=t_next,
-                                             text_index=text_index, coef=coef, bboxs_curr=bboxes)
+            with _nvtx_range(f"{self.method}_step_{i}_t{int(step)}"):
+                img, _, e_t = self.p_sample_plms(img, cond, int(step), index=index, unconditional_guidance_scale=scale,
+                                                 unconditional_conditioning=uc, old_eps=old_eps, t_next=t_next,
+                                                 text_index=text_index, coef=coef, bboxs_curr=bboxes)
             old_eps.append(e_t)
             if len(old_eps) >= 4:
                 old_eps.pop(0)
@@ -171,14 +190,18 @@ class PLMSSampler(object):
             if runner is not None:
                 runner.new_trajectory()
             with torch.set_grad_enabled(do_opt):
-                img = self._trajectory(img_input.clone(), cond, unconditional_conditioning,
-                                       unconditional_guidance_scale, W if n_obj else None, bboxes_arg, text_index)
+                with _nvtx_range(f"alpha_epoch_{epoch}_trajectory"):
+                    img = self._trajectory(img_input.clone(), cond, unconditional_conditioning,
+                                           unconditional_guidance_scale, W if n_obj else None, bboxes_arg, text_index)
                 if do_opt or self.save_images:
-                    decoded = self.decode_fn(img)  # (decode + 1) / 2 clamped to [0, 1]   (plms.py:249-250)
+                    with _nvtx_range("vae_decode"):
+                        decoded = self.decode_fn(img)  # (decode + 1) / 2 clamped to [0, 1]   (plms.py:249-250)
                 if do_opt:
-                    loss, per_prompt = self.loss_fn(decoded, texts, bboxes_pp, names_pp)
+                    with _nvtx_range("clip_loss"):
+                        loss, per_prompt = self.loss_fn(decoded, texts, bboxes_pp, names_pp)
                     optimizer.zero_grad(set_to_none=True)
-                    loss.backward()
+                    with _nvtx_range(f"alpha_epoch_{epoch}_backward"):
+                        loss.backward()
                     alpha_grads.append(W.grad.detach().clone())  # dL/dalpha of this epoch (diagnostics / parity tests)
                     optimizer.step()
                     losses.append([float(v) for v in torch.stack(per_prompt).detach().cpu()])
