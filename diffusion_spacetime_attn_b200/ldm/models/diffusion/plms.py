@@ -223,15 +223,45 @@ class PLMSSampler(object):
             Image.fromarray(arr[b]).save(os.path.join(self.out_dir, "final%d_s%d_index_%d.png" % (epoch, seed, idx or 0)))
 
     # ------------------------------------------------------------------------------------------------
-    def _model_output(self, x, t_int, c, uc, scale, text_index, coef, bboxs_curr):
-        """get_model_output (plms.py:299-308): rows [uncond x B, cond x B] through apply_model_extra, then CFG."""
+    def _model_eps(self, x, t_int, c, uc, text_index, coef, bboxs_curr):
+        """The UNet's two output rows [uncond x B, cond x B] through apply_model_extra (plms.py:304-307)."""
         B = x.shape[0]
         t_in = self._ts[t_int].expand(2 * B)
         x_in = torch.cat([x, x])
         c_in = torch.cat([uc, c])
-        e_t_uncond, e_t = self.model.apply_model_extra(x_in, text_index, t_in, c_in, coef=coef, bboxs_curr=bboxs_curr,
-                                                       step_time=t_int).chunk(2)
+        return self.model.apply_model_extra(x_in, text_index, t_in, c_in, coef=coef, bboxs_curr=bboxs_curr, step_time=t_int)
+
+    def _model_output(self, x, t_int, c, uc, scale, text_index, coef, bboxs_curr):
+        """get_model_output (plms.py:299-308): the two rows, then classifier-free guidance."""
+        e_t_uncond, e_t = self._model_eps(x, t_int, c, uc, text_index, coef, bboxs_curr).chunk(2)
         return e_t_uncond + scale * (e_t - e_t_uncond)
+
+    def _step_consts(self, index):
+        """(a_x, a_e, p_x, p_e) with x_prev = a_x x + a_e e' and pred_x0 = p_x x + p_e e' (plms.py:321-338, eta = 0)."""
+        a_t, a_prev = float(self.ddim_alphas[index]), float(self.ddim_alphas_prev[index])
+        sigma_t, sqrt_1m = float(self.ddim_sigmas[index]), float(self.ddim_sqrt_one_minus_alphas[index])
+        p_x, p_e = 1.0 / (a_t ** 0.5), -sqrt_1m / (a_t ** 0.5)
+        return (a_prev ** 0.5) * p_x, ((1.0 - a_prev - sigma_t ** 2) ** 0.5) + (a_prev ** 0.5) * p_e, p_x, p_e
+
+    _AB = {0: (1.0, ()), 1: (3 / 2, (-1 / 2,)), 2: (23 / 12, (-16 / 12, 5 / 12)), 3: (55 / 24, (-59 / 24, 37 / 24, -9 / 24))}
+
+    def _p_sample_fused(self, x, eps, index, scale, old_eps, model_eps_at):
+        """p_sample_plms with every elementwise operation of the step in ONE kernel launch (ops.plms_step) and one more in
+        backward; `eps` is the UNet output at (x, t), `model_eps_at(x_prev)` evaluates it at t_next (first PLMS step only)."""
+        from .... import ops as _ops
+
+        consts = self._step_consts(index)
+        if self.method == "ddim":
+            x_prev, e_t, pred = _ops.plms_step(eps, x, [], scale, 1.0, [], *consts)
+            return x_prev, pred, e_t
+        if len(old_eps) == 0:  # pseudo improved Euler: e' = (e_t + e_t_next) / 2 with the SAME coefficient column
+            x_mid, e_t, _ = _ops.plms_step(eps, x, [], scale, 1.0, [], *consts)
+            x_prev, _, pred = _ops.plms_step(model_eps_at(x_mid), x, [e_t], scale, 0.5, [0.5], *consts)
+            return x_prev, pred, e_t
+        k = min(len(old_eps), 3)
+        w_e, w_old = self._AB[k]
+        x_prev, e_t, pred = _ops.plms_step(eps, x, [old_eps[-1 - j] for j in range(k)], scale, w_e, list(w_old), *consts)
+        return x_prev, pred, e_t
 
     def _x_prev_and_pred_x0(self, x, e_t, index):
         a_t, a_prev = float(self.ddim_alphas[index]), float(self.ddim_alphas_prev[index])
@@ -246,9 +276,17 @@ class PLMSSampler(object):
                       text_index=None, coef=None, bboxs_curr=None):
         t_int = int(t if not torch.is_tensor(t) else t.flatten()[0].item())
         tn_int = int(t_next if not torch.is_tensor(t_next) else t_next.flatten()[0].item())
+        from .... import ops as _ops
+
+        eps = self._model_eps(x, t_int, c, unconditional_conditioning, text_index, coef, bboxs_curr)
+        if _ops.plms_step_usable(eps, x, old_eps[-3:]):
+            return self._p_sample_fused(
+                x, eps, index, unconditional_guidance_scale, old_eps,
+                lambda xp: self._model_eps(xp, tn_int, c, unconditional_conditioning, text_index, coef, bboxs_curr))
         out = lambda xx, tt: self._model_output(xx, tt, c, unconditional_conditioning, unconditional_guidance_scale,
                                                 text_index, coef, bboxs_curr)
-        e_t = out(x, t_int)
+        e_u0, e_c0 = eps.chunk(2)
+        e_t = e_u0 + unconditional_guidance_scale * (e_c0 - e_u0)
         if self.method == "ddim":
             e_t_prime = e_t
         elif len(old_eps) == 0:  # pseudo improved Euler: second evaluation with the SAME coefficient column

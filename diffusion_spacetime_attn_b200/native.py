@@ -28,6 +28,8 @@ EXPORTED_SYMBOLS = (
     "sta_geglu_bwd",
     "sta_upsample2x_fwd",
     "sta_upsample2x_bwd",
+    "sta_plms_step_fwd",
+    "sta_plms_step_bwd",
     "sta_probe_gemm",
     "sta_probe_tmem_bw",
     "sta_debug_read",
@@ -119,6 +121,22 @@ class Upsample2xArgs(C.Structure):
                 ("channels", C.c_int32)]
 
 
+class PlmsStepArgs(C.Structure):
+    _fields_ = [
+        ("eps", C.c_void_p), ("x", C.c_void_p), ("old", C.c_void_p * 3), ("e_t", C.c_void_p), ("x_prev", C.c_void_p),
+        ("pred_x0", C.c_void_p), ("prompts", C.c_int32), ("elems", C.c_int64), ("guidance", C.c_float), ("w_e", C.c_float),
+        ("w_old", C.c_float * 3), ("a_x", C.c_float), ("a_e", C.c_float), ("p_x", C.c_float), ("p_e", C.c_float),
+    ]
+
+
+class PlmsStepBwdArgs(C.Structure):
+    _fields_ = [
+        ("g_x_prev", C.c_void_p), ("g_e_t", C.c_void_p), ("g_eps", C.c_void_p), ("g_x", C.c_void_p), ("g_old", C.c_void_p * 3),
+        ("prompts", C.c_int32), ("elems", C.c_int64), ("guidance", C.c_float), ("w_e", C.c_float), ("w_old", C.c_float * 3),
+        ("a_x", C.c_float), ("a_e", C.c_float),
+    ]
+
+
 class ProbeArgs(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("a_rows", C.c_int32), ("a_tensor_rows", C.c_int32), ("a_cols", C.c_int32),
@@ -156,6 +174,7 @@ def load() -> C.CDLL:
         ("sta_add_layernorm_fwd", AddLayerNormArgs), ("sta_add_layernorm_bwd", AddLayerNormBwdArgs),
         ("sta_geglu_fwd", GegluArgs), ("sta_geglu_bwd", GegluArgs),
         ("sta_upsample2x_fwd", Upsample2xArgs), ("sta_upsample2x_bwd", Upsample2xArgs),
+        ("sta_plms_step_fwd", PlmsStepArgs), ("sta_plms_step_bwd", PlmsStepBwdArgs),
     ):
         if not hasattr(lib, name):  # reported by tests/test_cabi.py; calling it raises AttributeError
             continue

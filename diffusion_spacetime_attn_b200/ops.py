@@ -15,7 +15,7 @@ from . import native
 # number of kernels launched by this module since import (bench.py reports it as `gpu_launches`)
 LAUNCHES = {"sattn_fwd": 0, "sattn_bwd": 0, "xattn_fwd": 0, "xattn_bwd": 0, "groupnorm_fwd": 0, "groupnorm_bwd": 0,
             "add_layernorm_fwd": 0, "add_layernorm_bwd": 0, "geglu_fwd": 0, "geglu_bwd": 0,
-            "upsample2x_fwd": 0, "upsample2x_bwd": 0}
+            "upsample2x_fwd": 0, "upsample2x_bwd": 0, "plms_step_fwd": 0, "plms_step_bwd": 0}
 
 
 def launch_count() -> int:
@@ -620,3 +620,70 @@ class Upsample2xFn(torch.autograd.Function):
 def upsample_nearest2x(x):
     """F.interpolate(x, scale_factor=2, mode="nearest") for fp16 CUDA images (NHWC is free, NCHW is converted once)."""
     return Upsample2xFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------------
+# elementwise part of a PLMS / DDIM sampler step (csrc/sta_sampler.cu)
+# ------------------------------------------------------------------------------------------------------
+def plms_step_usable(eps: torch.Tensor, x: torch.Tensor, olds) -> bool:
+    """The fused kernel takes dense fp32 CUDA tensors (what the CUDA-graph UNet evaluation returns); anything else (fp16 eps
+    of the eager autocast path, CPU stand-in models of the host tests) stays on the sampler's torch expressions."""
+    ts = [eps, x, *olds]
+    return (all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in ts) and eps.shape[0] == 2 * x.shape[0]
+            and (x[0].numel() % 4) == 0 and all(t.shape == x.shape for t in olds) and len(olds) <= 3)
+
+
+class PlmsStepFn(torch.autograd.Function):
+    """(x_prev, e_t, pred_x0) of include/sta_b200.h::sta_plms_step_fwd; gradients flow to eps, x and the old estimates."""
+
+    @staticmethod
+    def forward(ctx, eps, x, old0, old1, old2, guidance, w_e, w_old, a_x, a_e, p_x, p_e):
+        olds = [old0, old1, old2]
+        B, elems = x.shape[0], x[0].numel()
+        e_t, x_prev, pred = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        a = native.PlmsStepArgs()
+        a.eps, a.x, a.e_t, a.x_prev, a.pred_x0 = eps.data_ptr(), x.data_ptr(), e_t.data_ptr(), x_prev.data_ptr(), pred.data_ptr()
+        for k in range(3):
+            a.old[k] = olds[k].data_ptr() if olds[k] is not None else None
+            a.w_old[k] = float(w_old[k]) if olds[k] is not None else 0.0
+        a.prompts, a.elems = B, elems
+        a.guidance, a.w_e, a.a_x, a.a_e, a.p_x, a.p_e = float(guidance), float(w_e), float(a_x), float(a_e), float(p_x), float(p_e)
+        with _timed("plms_step_fwd", (B, elems)):
+            native.check(native.load().sta_plms_step_fwd(C.byref(a), _stream()), "sta_plms_step_fwd")
+        LAUNCHES["plms_step_fwd"] += 1
+        ctx.consts = (B, elems, float(guidance), float(w_e), [float(w) for w in w_old], float(a_x), float(a_e))
+        ctx.has_old = [o is not None for o in olds]
+        ctx.mark_non_differentiable(pred)
+        ctx.set_materialize_grads(False)
+        return x_prev, e_t, pred
+
+    @staticmethod
+    def backward(ctx, g_x_prev, g_e_t, _g_pred):
+        B, elems, guidance, w_e, w_old, a_x, a_e = ctx.consts
+        ref = g_x_prev if g_x_prev is not None else g_e_t
+        if ref is None:
+            return (None,) * 12
+        g_x_prev = g_x_prev.contiguous() if g_x_prev is not None else None
+        g_e_t = g_e_t.contiguous() if g_e_t is not None else None
+        g_eps = torch.empty((2 * B,) + tuple(ref.shape[1:]), device=ref.device, dtype=torch.float32)
+        g_x = torch.empty_like(ref)
+        g_old = [torch.empty_like(ref) if h else None for h in ctx.has_old]
+        a = native.PlmsStepBwdArgs()
+        a.g_x_prev = g_x_prev.data_ptr() if g_x_prev is not None else None
+        a.g_e_t = g_e_t.data_ptr() if g_e_t is not None else None
+        a.g_eps, a.g_x = g_eps.data_ptr(), g_x.data_ptr()
+        for k in range(3):
+            a.g_old[k] = g_old[k].data_ptr() if g_old[k] is not None else None
+            a.w_old[k] = w_old[k] if g_old[k] is not None else 0.0
+        a.prompts, a.elems, a.guidance, a.w_e, a.a_x, a.a_e = B, elems, guidance, w_e, a_x, a_e
+        with _timed("plms_step_bwd", (B, elems)):
+            native.check(native.load().sta_plms_step_bwd(C.byref(a), _stream()), "sta_plms_step_bwd")
+        LAUNCHES["plms_step_bwd"] += 1
+        return (g_eps, g_x, g_old[0], g_old[1], g_old[2]) + (None,) * 7
+
+
+def plms_step(eps, x, olds, guidance, w_e, w_old, a_x, a_e, p_x, p_e):
+    """One fused sampler step: eps [2B, ...] (uncond rows first), x [B, ...], olds = [e_{t-1}, e_{t-2}, e_{t-3}][:k]."""
+    o = list(olds) + [None] * (3 - len(olds))
+    w = list(w_old) + [0.0] * (3 - len(w_old))
+    return PlmsStepFn.apply(eps, x, o[0], o[1], o[2], guidance, w_e, w, a_x, a_e, p_x, p_e)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define STA_B200_VERSION 101 /* major*100 + minor */
+#define STA_B200_VERSION 102 /* major*100 + minor */
 
 /* return codes */
 #define STA_OK 0
@@ -255,6 +255,49 @@ typedef struct {
 
 int sta_upsample2x_fwd(const sta_upsample2x_args* args, void* stream);
 int sta_upsample2x_bwd(const sta_upsample2x_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Elementwise part of one PLMS / DDIM sampler step (PLMSSampler.p_sample_plms, ldm/models/diffusion/plms.py:296-358):
+ * classifier-free guidance of the UNet's two output rows (:304-308), the Adams-Bashforth combination with up to three
+ * previous noise estimates (:341-354) and the eta = 0 update of x (:321-338) in ONE launch, and their gradients in one.
+ *   eps      f32 [2*B, elems]   UNet output: rows [0,B) unconditional, [B,2B) conditional (elems = C*H*W per prompt)
+ *   x        f32 [B, elems]     current latent;   old[k]  f32 [B, elems] = e_{t-1-k} or NULL
+ *   e_t      = (1 - guidance) eps_u + guidance eps_c                 (out, kept by the caller as the next old[0])
+ *   e'       = w_e e_t + sum_k w_old[k] old[k]                       (AB weights, e.g. 55/24, -59/24, 37/24, -9/24)
+ *   x_prev   = a_x x + a_e e'       pred_x0 = p_x x + p_e e'  (optional)
+ * Backward: g_x_prev, g_e_t (either may be NULL = 0) -> g_eps [2*B, elems], g_x, g_old[k] (NULL where old[k] was NULL).
+ * Everything fp32, dense, 16-byte aligned; elems a multiple of 4.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* eps;
+  const void* x;
+  const void* old[3];
+  void* e_t;
+  void* x_prev;
+  void* pred_x0;
+  int32_t prompts;
+  int64_t elems;
+  float guidance, w_e;
+  float w_old[3];
+  float a_x, a_e, p_x, p_e;
+} sta_plms_step_args;
+
+int sta_plms_step_fwd(const sta_plms_step_args* args, void* stream);
+
+typedef struct {
+  const void* g_x_prev;
+  const void* g_e_t;
+  void* g_eps;
+  void* g_x;
+  void* g_old[3];
+  int32_t prompts;
+  int64_t elems;
+  float guidance, w_e;
+  float w_old[3];
+  float a_x, a_e;
+} sta_plms_step_bwd_args;
+
+int sta_plms_step_bwd(const sta_plms_step_bwd_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Test hook: one tcgen05 GEMM tile with caller-supplied UMMA descriptors (tests/test_probe_gpu.py pins the

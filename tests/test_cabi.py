@@ -63,7 +63,8 @@ def test_null_arguments_are_rejected_without_touching_the_gpu(lib):
                                           ("ProbeArgs", "sta_probe_args"), ("GroupNormArgs", "sta_groupnorm_args"),
                                           ("AddLayerNormArgs", "sta_add_layernorm_args"),
                                           ("AddLayerNormBwdArgs", "sta_add_layernorm_bwd_args"),
-                                          ("GegluArgs", "sta_geglu_args"), ("Upsample2xArgs", "sta_upsample2x_args")])
+                                          ("GegluArgs", "sta_geglu_args"), ("Upsample2xArgs", "sta_upsample2x_args"),
+                                          ("PlmsStepArgs", "sta_plms_step_args"), ("PlmsStepBwdArgs", "sta_plms_step_bwd_args")])
 def test_ctypes_structs_mirror_the_header(struct, cname):
     from diffusion_spacetime_attn_b200 import native
 
@@ -83,7 +84,8 @@ def test_ctypes_structs_mirror_the_header(struct, cname):
 STRUCTS = {"SattnFwdArgs": "sta_sattn_fwd_args", "SattnBwdArgs": "sta_sattn_bwd_args", "XattnFwdArgs": "sta_xattn_fwd_args",
            "XattnBwdArgs": "sta_xattn_bwd_args", "GroupNormArgs": "sta_groupnorm_args", "ProbeArgs": "sta_probe_args",
            "AddLayerNormArgs": "sta_add_layernorm_args", "AddLayerNormBwdArgs": "sta_add_layernorm_bwd_args",
-           "GegluArgs": "sta_geglu_args", "Upsample2xArgs": "sta_upsample2x_args"}
+           "GegluArgs": "sta_geglu_args", "Upsample2xArgs": "sta_upsample2x_args",
+           "PlmsStepArgs": "sta_plms_step_args", "PlmsStepBwdArgs": "sta_plms_step_bwd_args"}
 
 
 def test_ctypes_struct_sizes_and_offsets_match_the_c_compiler(tmp_path):
