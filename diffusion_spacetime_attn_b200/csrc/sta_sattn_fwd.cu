@@ -17,6 +17,11 @@
 #include "sta_common.cuh"
 #include "sta_host.h"
 
+// softmax threads per query row.  Measured on B200 (L0 / L1 / N=9216, us): 1: 111.6 / 22.5 / 434.9   2: 110.6 / 21.4 / 432.1
+// — no gain from four instead of two softmax warps per scheduler, so the simpler layout stays the default.
+#ifndef STA_FWD_SPLIT
+#define STA_FWD_SPLIT 1
+#endif
 #ifndef STA_POLY_EVERY
 #define STA_POLY_EVERY 0  // k > 0: 1 pair in k on the FMA pipe.  Measured on B200 (L0, us): 0: 111.6, 6: 115.7, 4: 117.8, 3: 130.0, 2: 150.7 -> off
 #endif
@@ -34,7 +39,8 @@ struct SattnCfg {
   static constexpr int VS = (NBLK == 1) ? 3 : (NBLK == 2 ? 2 : 1);
   static constexpr int TILE_BYTES = NBLK * kBlockBytes;
   static constexpr int SMEM_BYTES = (NQ + KS + VS) * TILE_BYTES + 1024;
-  static constexpr int THREADS = 64 + 128 * NQ;
+  static constexpr int SW = STA_FWD_SPLIT;          // softmax threads per query row (1 or 2)
+  static constexpr int THREADS = 64 + 128 * NQ * SW;
   // TMEM columns: S_r at 128 r.  When they fit, the packed-fp16 P_r tiles get their OWN 64 columns (SEP_P) instead
   // of aliasing S_r: the next S_r = Q_r K_{j+1}^T can then be issued as soon as the softmax warps have READ S_r,
   // i.e. it overlaps the exp phase instead of following the P V MMAs.  d=40: 256 + 128 + 96 = 480, d=160: 128 + 64 +
@@ -73,6 +79,7 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __shared__ uint64_t s_full[NQ], s_consumed[NQ], p_ready[NQ], pv_done[NQ];
   __shared__ uint32_t tmem_base_s;
   __shared__ int dead;
+  __shared__ float xmax[2][NQ][2][128], xsum[NQ][2][128];  // row statistics exchanged between the two halves of a row (SW = 2)
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int q0 = blockIdx.x * (128 * p.q_per_cta), h = blockIdx.y, b = blockIdx.z;
@@ -87,7 +94,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < NQ; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_consumed[i], 4); mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_consumed[i], 4 * Cfg::SW); mbar_init(&p_ready[i], 4 * Cfg::SW);
+      mbar_init(&pv_done[i], 1);
     }
     mbar_fence_init();
   }
@@ -209,44 +217,56 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
   } else {
     // ===================================== softmax / epilogue ================================
-    const int r = (warp - 2) >> 2;  // query tile of this warp
+    // SW threads per query row (SW = 2: the 128 score columns of a row are split between two warpgroups, which share the
+    // running reference maximum through shared memory — one 256-thread named barrier per key tile — and add their partial
+    // row sums once, in the epilogue).  Built to test whether four softmax warps per scheduler hide each other's TMEM-load /
+    // MUFU / pack latencies better than two: they do not (see STA_FWD_SPLIT above), the default is one thread per row.
+    constexpr int SW = Cfg::SW, CW = 128 / SW, NCH = DMMA / 8;
+    const int sw = warp - 2;
+    const int r = sw / (4 * SW);      // query tile of this warp
+    const int half = (sw >> 2) % SW;  // score columns [CW * half, CW * half + CW) of every key tile
     if (r < nq_active) {
       const int row_in_tile = ((warp & 3) << 5) + lane;
       const int row = q0 + r * 128 + row_in_tile;
       const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
-      const uint32_t s_addr = lane_addr + r * 128;
-      const uint32_t p_addr = lane_addr + Cfg::TMEM_P + r * Cfg::P_STRIDE;
+      const uint32_t s_addr = lane_addr + r * 128 + half * CW;
+      const uint32_t p_addr = lane_addr + Cfg::TMEM_P + r * Cfg::P_STRIDE + half * (CW / 2);
       const uint32_t o_addr = lane_addr + Cfg::TMEM_O + r * DMMA;
+      const int oc0 = half * NCH / SW, oc1 = (half + 1) * NCH / SW;  // 8-column chunks of O owned by this thread
       float m_ref = -INFINITY, l = 0.f;
       bool ok = true;
       for (int j = 0; j < T; ++j) {
         ok = mbar_wait_warp(&s_full[r], j & 1, &dead, p.err, 30);
         if (!ok) break;
         tc_fence_after();
-        uint32_t s[128];
-        tmem_ld32(s_addr, s);
-        tmem_ld32(s_addr + 32, s + 32);
-        tmem_ld32(s_addr + 64, s + 64);
-        tmem_ld32(s_addr + 96, s + 96);
+        uint32_t s[CW];
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 32) tmem_ld32(s_addr + c0, s + c0);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_consumed[r]);  // S_r is in registers: the tensor core may overwrite it
-        const int valid = n - j * 128;  // keys of this tile that exist
-        if (valid < 128) {
+        const int valid = n - j * 128 - half * CW;  // keys of this slice that exist
+        if (valid < CW) {
 #pragma unroll
-          for (int c = 0; c < 128; ++c)
+          for (int c = 0; c < CW; ++c)
             if (c >= valid) s[c] = 0xff800000u;  // -inf
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 128; c += 4) {
+        for (int c = 0; c < CW; c += 4) {
           mx0 = fmaxf(mx0, __uint_as_float(s[c]));
           mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
           mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        float mxl = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (SW == 2) {  // row maximum over both halves (double-buffered exchange: one barrier per key tile)
+          xmax[j & 1][r][half][row_in_tile] = mxl;
+          named_bar_sync(1 + r, 256);
+          mxl = fmaxf(mxl, xmax[j & 1][r][half ^ 1][row_in_tile]);
+        }
+        const float mx = mxl * p.scale_log2;
         if (j == 0) {
           m_ref = mx;
         } else {
@@ -260,21 +280,20 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const float f = need ? fast_exp2(m_ref - mx) : 1.f;
             if (need) m_ref = mx;
             l *= f;
-#pragma unroll
-            for (int c0 = 0; c0 < DMMA; c0 += 16) {
-              uint32_t o[16];
-              tmem_ld16(o_addr + c0, o);
+            for (int ch = oc0; ch < oc1; ++ch) {
+              uint32_t o[8];
+              tmem_ld8(o_addr + ch * 8, o);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-              tmem_st16(o_addr + c0, o);
+              for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st8(o_addr + ch * 8, o);
             }
             tmem_st_wait();
           }
         }
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 128; c += 2) {  // exp in place: the packed pair (c, c+1) lands in s[c/2]
+        for (int c = 0; c < CW; c += 2) {  // exp in place: the packed pair (c, c+1) lands in s[c/2]
           // every STA_POLY_EVERY-th pair is evaluated on the FMA pipe instead of the MUFU pipe (see poly_exp2)
           const bool poly = (STA_POLY_EVERY > 0) && ((c >> 1) % (STA_POLY_EVERY > 0 ? STA_POLY_EVERY : 1) == (STA_POLY_EVERY - 1));
           const float x0 = fmaf(__uint_as_float(s[c]), p.scale_log2, -m_ref);
@@ -290,10 +309,8 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (!ok) break;
           tc_fence_after();
         }
-        tmem_st16(p_addr, s);
-        tmem_st16(p_addr + 16, s + 16);
-        tmem_st16(p_addr + 32, s + 32);
-        tmem_st16(p_addr + 48, s + 48);
+#pragma unroll
+        for (int c0 = 0; c0 < CW / 2; c0 += 16) tmem_st16(p_addr + c0, s + c0);
         l += l0 + l1;
         tmem_st_wait();
         tc_fence_before();
@@ -302,15 +319,20 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       // -------- epilogue: O / l -> fp16, natural-log LSE --------
       ok = __all_sync(0xffffffffu, ok);
+      if (SW == 2) {  // total row sum = the two halves' partial sums (taken with the same reference maximum)
+        xsum[r][half][row_in_tile] = l;
+        named_bar_sync(1 + r, 256);
+        l += xsum[r][half ^ 1][row_in_tile];
+      }
       if (ok) ok = mbar_wait_warp(&pv_done[r], (T - 1) & 1, &dead, p.err, 31);
       if (ok) {
         tc_fence_after();
         const float inv = 1.f / l;
         __half* orow = p.out + (long long)b * p.o_batch_stride + (long long)row * p.o_token_stride + h * D;
-#pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 8) {
+        for (int ch = oc0; ch < oc1; ++ch) {
+          if (ch * 8 >= D) break;
           uint32_t o[8];
-          tmem_ld8(o_addr + c0, o);
+          tmem_ld8(o_addr + ch * 8, o);
           tmem_ld_wait();
           if (row < n) {
             uint4 v;
@@ -318,10 +340,10 @@ sattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             v.y = pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
             v.z = pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
             v.w = pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-            *reinterpret_cast<uint4*>(orow + c0) = v;
+            *reinterpret_cast<uint4*>(orow + ch * 8) = v;
           }
         }
-        if (p.lse && row < n)
+        if (p.lse && row < n && half == 0)
           p.lse[((long long)b * p.heads + h) * n + row] = (m_ref + log2f(l)) * 0.6931471805599453f;
       }
     }
