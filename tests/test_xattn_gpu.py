@@ -167,3 +167,44 @@ def test_xattn_context_lengths_other_than_77(ctx_len, d):
     _close(d_q, qf.grad, atol=3e-3, rtol=2e-2)
     rel = (d_coef.cpu() - cf.grad).abs() / (cf.grad.abs() + 1e-2 * cf.grad.abs().max() + 1e-6)
     assert rel.max().item() < 2e-2
+
+
+@pytest.mark.gpu
+def test_xattn_maximum_object_count_and_limits():
+    """n_obj = 8 is the library's maximum (every object live in some tiles, dead in others: ring refills + skips);
+    9 objects, 81 context tokens or an unsupported head dim are ERRORS, never a fallback."""
+    B, n, h, d, n_obj = 1, 1024, 2, 80, 8
+    g = torch.Generator().manual_seed(77)
+    C = h * d
+    q = torch.randn(2 * B, n, C, generator=g).half()
+    k = torch.randn(B, 2 + n_obj, 77, C, generator=g).half()
+    v = torch.randn(B, 2 + n_obj, 77, C, generator=g).half()
+    centers = [[0.15 + 0.1 * i, 0.2 + 0.08 * i] for i in range(n_obj)]
+    masks = O.flat_masks(centers, n).unsqueeze(0)
+    coef = (torch.rand(B, n_obj, generator=g) * 2 + 0.5).float()
+    d_out = (torch.randn(2 * B, n, C, generator=g) * 0.1).half()
+    qf, cf = q.float().requires_grad_(True), coef.clone().requires_grad_(True)
+    ref = O.dual_cross_attention_core(qf, k.float(), v.float(), masks, cf, h)
+    (ref * d_out.float()).sum().backward()
+    dev = lambda t: t.cuda()
+    out, lse = ops.xattn_fwd(dev(q), dev(k), dev(v), dev(masks), dev(coef), h)
+    d_q, d_coef = ops.xattn_bwd(dev(q), dev(k), dev(v), dev(masks), dev(coef), lse, dev(d_out), h, out=out)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    _close(out, ref.detach())
+    _close(d_q, qf.grad, atol=3e-3, rtol=2e-2)
+    rel = (d_coef.cpu() - cf.grad).abs() / (cf.grad.abs() + 1e-2 * cf.grad.abs().max() + 1e-6)
+    assert rel.max().item() < 2e-2
+    # limits
+    k9 = torch.randn(B, 2 + 9, 77, C).half().cuda()
+    with pytest.raises(RuntimeError, match="n_obj"):
+        ops.xattn_fwd(dev(q), k9, k9, torch.zeros(B, 9, n, dtype=torch.uint8).cuda(), torch.ones(B, 9).cuda(), h)
+    k81 = torch.randn(B, 2, 81, C).half().cuda()
+    with pytest.raises(RuntimeError, match="ctx_len"):
+        ops.xattn_fwd(dev(q), k81, k81, None, None, h)
+    q56 = torch.randn(2, 128, 2 * 56).half().cuda()
+    k56 = torch.randn(1, 2, 77, 2 * 56).half().cuda()
+    with pytest.raises(RuntimeError, match="head_dim"):
+        ops.xattn_fwd(q56, k56, k56, None, None, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.xattn_fwd(q, dev(k), dev(v), dev(masks), dev(coef), h)
