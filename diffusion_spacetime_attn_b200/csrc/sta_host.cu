@@ -133,7 +133,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 }
 
 int make_tmap_f32_dense(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                        const uint32_t* box) {
+                        const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(STA_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[5], gstr[5];
@@ -144,9 +144,10 @@ int make_tmap_f32_dense(CUtensorMap* out, const void* base, int rank, const uint
     es[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i];
   }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(STA_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r);
   return STA_OK;
 }

@@ -58,6 +58,6 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 // Tiled fp32 tensor map WITHOUT swizzle (dense box rows), used as the destination of TMA reduce-add.
 int make_tmap_f32_dense(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                        const uint32_t* box);
+                        const uint32_t* box, int swizzle_bytes = 0);  // 0 (dense rows), 32 or 64: smem-side XOR swizzle
 
 }  // namespace sta

@@ -296,9 +296,14 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           uint32_t o[8];
           tmem_ld8(src + cbase + c0, o);
           tmem_ld_wait();
-          float4* d4 = reinterpret_cast<float4*>(stage + r * wcols + c0);
-          d4[0] = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
-          d4[1] = make_float4(__uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]), __uint_as_float(o[7]));
+          // rows of 64 B (W0 = 16 floats) / 32 B (W1 = 8): thread r of a warp writes row r, so without a swizzle the eight
+          // threads of a store phase hit 2 (4) bank groups — 4-way (2-way) conflicts, 5.5 M extra wavefronts per launch in
+          // ncu.  The TMA maps use SWIZZLE_64B / SWIZZLE_32B (16-byte chunk index ^= address bits [7,8] / [7]).
+          const int ch = c0 >> 2;  // first 16-byte chunk of this 8-float group
+          const int sx = (wcols == 16) ? ((r >> 1) & 3) : ((r >> 2) & 1);
+          float4* row4 = reinterpret_cast<float4*>(stage + r * wcols);
+          row4[ch ^ sx] = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
+          row4[(ch + 1) ^ sx] = make_float4(__uint_as_float(o[4]), __uint_as_float(o[5]), __uint_as_float(o[6]), __uint_as_float(o[7]));
         }
         fence_proxy_async_smem();
         named_bar_sync(5 + NWG + g, 128);
@@ -541,8 +546,10 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   {
     const uint64_t st[4] = {4, (uint64_t)D * 4, (uint64_t)C * 4, (uint64_t)a->n * C * 4};
     const uint32_t bx0[4] = {(uint32_t)Cfg::DQ_W0, 1, 128, 1}, bx1[4] = {(uint32_t)Cfg::DQ_W1, 1, 128, 1};
-    if ((rc = make_tmap_f32_dense(&tm_dq, a->dq_accum, 4, dims, st, bx0))) return rc;
-    if ((rc = make_tmap_f32_dense(&tm_dq1, a->dq_accum, 4, dims, st, bx1))) return rc;
+    // PIPE_DRAIN stages 64-byte / 32-byte rows with the matching shared-memory swizzle (bank-conflict-free stores)
+    const int sw0 = (Cfg::PIPE_DRAIN && Cfg::DQ_W0 == 16) ? 64 : 0, sw1 = (Cfg::PIPE_DRAIN && Cfg::DQ_W1 == 8) ? 32 : 0;
+    if ((rc = make_tmap_f32_dense(&tm_dq, a->dq_accum, 4, dims, st, bx0, sw0))) return rc;
+    if ((rc = make_tmap_f32_dense(&tm_dq1, a->dq_accum, 4, dims, st, bx1, sw1))) return rc;
   }
   STA_CUDA_CHECK(cudaMemsetAsync(a->dq_accum, 0, sizeof(float) * a->batch * a->n * C, stream));
   sattn_delta_kernel<D><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
