@@ -351,3 +351,65 @@ class GraphedModelRunner:
 
     def slot_summary(self) -> dict:
         return {str(k): {"slots": len(g.slots), "slot_gib": round(g.slot_bytes / 2 ** 30, 3)} for k, g in self.graphs.items()}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# A fixed-shape differentiable function as one (forward-with-grad, backward) CUDA-graph pair — used for the KL-VAE decode
+# of the alpha-optimisation tail (reference ddpm.py:706-763 through plms.py:249-250), ~1000 eager launches per epoch.
+# ----------------------------------------------------------------------------------------------------------
+class _GraphedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, owner: "GraphedDifferentiable"):
+        ctx.owner = owner
+        owner.x.copy_(x)
+        owner.g_fwd.replay()
+        owner.pending = True
+        return owner.y.clone()
+
+    @staticmethod
+    def backward(ctx, d_y):
+        o = ctx.owner
+        if not o.pending:
+            raise RuntimeError("GraphedDifferentiable: backward without a matching forward (one call in flight at a time)")
+        o.d_y.copy_(d_y)
+        o.g_bwd.replay()
+        o.pending = False
+        return o.dx.clone(), None
+
+
+class GraphedDifferentiable:
+    """`fn`: tensor [shape] -> tensor, frozen weights, fixed shapes.  One call may be in flight at a time (its saved
+    activations live in the graph pool until its backward has been replayed) — exactly the sampler's use: decode once per
+    epoch, back-propagate, repeat."""
+
+    def __init__(self, fn, example: torch.Tensor, warmup: int = 2):
+        self.fn = fn
+        self.x = example.detach().clone()
+        self.pending = False
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.enable_grad():
+            for _ in range(warmup):
+                xg = self.x.detach().requires_grad_(True)
+                y = fn(xg)
+                torch.autograd.grad(y, xg, torch.ones_like(y))
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        with torch.enable_grad():
+            xg = self.x.detach().requires_grad_(True)  # a view of the static input buffer
+            self.g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fwd, pool=pool):
+                y = fn(xg)
+            self.d_y = torch.zeros_like(y)
+            self.g_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_bwd, pool=pool):
+                (dx,) = torch.autograd.grad(y, xg, self.d_y)
+        self.y, self.dx = y.detach(), dx
+        torch.cuda.synchronize()
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if not torch.is_grad_enabled() or not x.requires_grad:
+            with torch.no_grad():
+                return self.fn(x)
+        return _GraphedFn.apply(x, self)

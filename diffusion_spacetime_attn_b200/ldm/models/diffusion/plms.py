@@ -77,8 +77,38 @@ class PLMSSampler(object):
         self.save_images, self.out_dir, self.verbose = save_images, out_dir, verbose
         # test hooks: replace the VAE decode / CLIP loss by any differentiable stand-ins (both are outside the kernels)
         self.loss_fn = loss_fn or self._loss
-        self.decode_fn = decode_fn or (lambda z: torch.clamp((self.model.decode_first_stage(z) + 1.0) / 2.0, 0.0, 1.0))
+        self.decode_fn = decode_fn or self._decode
+        self._graphed_decode = {}  # latent shape -> graphed.GraphedDifferentiable (CUDA-graph execution only)
         self.last_result = None
+
+    # ------------------------------------------------------------------------------------------------
+    # Larger decodes (config 5: 2 x 96 x 96) stay eager: their saved activations would sit in a private graph pool for the
+    # life of the pipeline next to 27 activation slots that already fill the GPU.
+    GRAPHED_DECODE_MAX_LATENT = 2 * 64 * 64
+
+    def _decode_eager(self, z):
+        return torch.clamp((self.model.decode_first_stage(z) + 1.0) / 2.0, 0.0, 1.0)  # plms.py:249-250
+
+    def _decode(self, z):
+        """decode_first_stage + the clamp to [0, 1].  When the UNet runs under CUDA graphs (the model carries a graph runner)
+        the differentiable decode — fixed shapes, frozen weights, ~1000 eager launches forward + backward — is one captured
+        (forward-with-grad, backward) graph pair per latent shape."""
+        graphable = (getattr(self.model, "graph_runner", None) is not None and z.is_cuda and torch.is_grad_enabled()
+                     and z.requires_grad and z.shape[0] * z.shape[2] * z.shape[3] <= self.GRAPHED_DECODE_MAX_LATENT
+                     and os.environ.get("STA_GRAPH_DECODE", "1") != "0")
+        if not graphable:
+            return self._decode_eager(z)
+        key = (tuple(z.shape), z.dtype)
+        g = self._graphed_decode.get(key)
+        if g is None:
+            from ....graphed import GraphedDifferentiable
+
+            def fn(zz):
+                with torch.autocast("cuda", dtype=torch.float16):
+                    return self._decode_eager(zz)
+
+            g = self._graphed_decode[key] = GraphedDifferentiable(fn, z.detach())
+        return g(z)
 
     # ------------------------------------------------------------------------------------------------
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0.0, verbose=True):

@@ -67,3 +67,45 @@ def test_decoder_fused_fp16_path_matches_reference():
     assert ops.launch_count() - before > 100, "the fused kernels did not run"
     e_img, e_dz = _rel(img, img_ref), _rel(zd.grad, dz_ref)
     assert e_img < 5e-3 and e_dz < 2e-2, (e_img, e_dz)
+
+
+@pytest.mark.gpu
+def test_graphed_decode_replays_the_eager_decode():
+    """graphed.GraphedDifferentiable (the captured forward-with-grad / backward pair the sampler uses for the alpha-optimisation
+    tail): several replays with fresh inputs reproduce the eager fp16 decode and its latent gradient (same kernels, same
+    order; GroupNorm statistics use atomics, so equality is to fp16 rounding, not bitwise), and still match the reference."""
+    from diffusion_spacetime_attn_b200 import native
+    from diffusion_spacetime_attn_b200.graphed import GraphedDifferentiable
+
+    dec, z, G, img_ref, dz_ref = _decoder_and_inputs()
+    dec = dec.cuda().half().requires_grad_(False)
+    for m in dec.modules():
+        if isinstance(m, torch.nn.GroupNorm):
+            m.float()
+    dec.to(memory_format=torch.channels_last)
+
+    def fn(zz):
+        with torch.autocast("cuda", dtype=torch.float16):
+            return torch.clamp((dec(zz) + 1.0) / 2.0, 0.0, 1.0)
+
+    Gd = G.cuda()
+    graphed = GraphedDifferentiable(fn, z.cuda())
+    gen = torch.Generator().manual_seed(5)
+    for k in range(3):
+        zk = (z if k == 2 else torch.randn(z.shape, generator=gen)).cuda()
+        za, zb = zk.clone().requires_grad_(True), zk.clone().requires_grad_(True)
+        ia = fn(za)
+        (ia.float() * Gd).sum().backward()
+        ib = graphed(zb)
+        (ib.float() * Gd).sum().backward()
+        torch.cuda.synchronize()
+        assert ib.dtype == ia.dtype and ib.shape == ia.shape
+        assert _rel(ib, ia.detach().float().cpu()) < 1e-3 and _rel(zb.grad, za.grad.float().cpu()) < 5e-3
+    assert native.device_error() == 0
+    with torch.no_grad():  # no graph needed: plain call
+        assert _rel(graphed(z.cuda()), ia.detach().float().cpu()) < 1e-3
+    with pytest.raises(RuntimeError, match="backward without a matching forward"):
+        zc = z.cuda().requires_grad_(True)
+        out = graphed(zc)
+        out.sum().backward(retain_graph=True)
+        out.sum().backward()
