@@ -27,6 +27,8 @@ constexpr int kGnUnroll = 4;        // independent 16-byte loads in flight per t
 struct GnParams {
   const __half* x;    // [B, HW, C] (NHWC)
   const __half* dy;   // backward only
+  const __half* dres; // backward only, optional [B, HW, C]: a second gradient of x (residual branch), added to dx
+  long long dres_stride;  // elements between its rows (>= C: it may be a channel slice of a wider NHWC tensor)
   const __half* xb;   // optional fp16 [B, C]: added to x before everything else (conv bias + timestep embedding)
   long long xb_stride;  // elements between the rows of xb (>= C)
   const float* gamma;
@@ -289,13 +291,14 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_apply_kernel(GnParams p)
   const long long off = ((long long)b * p.hw) * p.c + m.c0;
   constexpr int U = 2;
   for (int r = r0 + m.lane; r < r1; r += U * m.lanes) {
-    uint4 vx[U], vd[U];
+    uint4 vx[U], vd[U], vr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int rr = r + u * m.lanes;
       if (rr < r1) {
         vx[u] = *reinterpret_cast<const uint4*>(p.x + off + (long long)rr * p.c);
         vd[u] = *reinterpret_cast<const uint4*>(p.dy + off + (long long)rr * p.c);
+        if (p.dres) vr[u] = *reinterpret_cast<const uint4*>(p.dres + ((long long)b * p.hw + rr) * p.dres_stride + m.c0);
       }
     }
 #pragma unroll
@@ -311,6 +314,11 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_apply_kernel(GnParams p)
           float dz = d[i];
           if (SILU) dz *= dsilu_f(fmaf(xh, k.gam[i], k.bet[i]));
           f[i] = k.rstd[i] * (dz * k.gam[i] - m1[i] - xh * m2[i]);
+        }
+        if (p.dres) {
+          unpack8(vr[u], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += d[i];
         }
         *reinterpret_cast<uint4*>(p.out + off + (long long)rr * p.c) = pack8(f);
       }
@@ -356,6 +364,8 @@ static int gn_launch_shape(const sta_groupnorm_args* a, GnLaunch* L) {
 struct GnClusterParams {
   const __half* x;
   const __half* dy;
+  const __half* dres;  // backward only, optional: added to dx (the gradient of x's other consumer)
+  long long dres_stride;  // elements between its rows (>= c)
   const __half* xb;
   long long xb_stride;
   const float* gamma;
@@ -577,6 +587,14 @@ __global__ void __launch_bounds__(640) gn_cluster_bwd_kernel(GnClusterParams p) 
   // dx = rs * (dxhat - m1 - xhat * m2) = dxhat * rs - q - xhat * pm,  q = rs * m1,  pm = rs * m2
   const float q_lo = rs_lo * tot[2 * gl0] * inv_n, pm_lo = rs_lo * tot[2 * gl0 + 1] * inv_n;
   const float q_hi = nb < 8 ? rs_hi * tot[2 * gl0 + 2] * inv_n : 0.f, pm_hi = nb < 8 ? rs_hi * tot[2 * gl0 + 3] * inv_n : 0.f;
+  uint4 vres[R];
+  if (p.dres) {  // all R loads in flight before the first use
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int rr = r0 + lane_row + u * p.lanes;
+      if (rr < r1) vres[u] = *reinterpret_cast<const uint4*>(p.dres + ((long long)b * p.hw + rr) * p.dres_stride + ch0);
+    }
+  }
 #pragma unroll
   for (int u = 0; u < R; ++u) {
     const int rr = r0 + lane_row + u * p.lanes;
@@ -588,6 +606,11 @@ __global__ void __launch_bounds__(640) gn_cluster_bwd_kernel(GnClusterParams p) 
       for (int i = 0; i < 8; ++i) {
         const float t = fmaf(d[i], i < nb ? rs_lo : rs_hi, -(i < nb ? q_lo : q_hi));
         f[i] = fmaf(-f[i], i < nb ? pm_lo : pm_hi, t);
+      }
+      if (p.dres) {
+        unpack8(vres[u], d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += d[i];
       }
       *reinterpret_cast<uint4*>(p.out + off + (long long)rr * p.c) = pack8(f);
     }
@@ -643,6 +666,8 @@ static int gn_cluster(const sta_groupnorm_args* a, bool bwd, cudaStream_t s, boo
   GnClusterParams p{};
   p.x = reinterpret_cast<const __half*>(a->x);
   p.dy = reinterpret_cast<const __half*>(a->d_out);
+  p.dres = bwd ? reinterpret_cast<const __half*>(a->d_res) : nullptr;
+  p.dres_stride = a->d_res_stride > 0 ? a->d_res_stride : a->channels;
   p.xb = reinterpret_cast<const __half*>(a->x_bias);
   p.xb_stride = a->x_bias_stride > 0 ? a->x_bias_stride : a->channels;
   p.gamma = a->gamma; p.beta = a->beta;
@@ -709,6 +734,9 @@ extern "C" int sta_groupnorm_bwd(const sta_groupnorm_args* a, void* stream) {
   using namespace sta;
   if (!a || !a->x || !a->d_out || !a->out || !a->gamma || !a->beta || !a->stats || !a->bwd_stats)
     return fail(STA_ERR_BAD_ARG, "sta_groupnorm_bwd: null pointer");
+  if (a->d_res && ((reinterpret_cast<uintptr_t>(a->d_res) & 15u) || a->d_res_stride < 0 || a->d_res_stride % 8 ||
+                   (a->d_res_stride > 0 && a->d_res_stride < a->channels)))
+    return fail(STA_ERR_BAD_ARG, "sta_groupnorm_bwd: d_res must be 16-byte aligned with a row stride that is 0 or a multiple of 8 >= channels");
   GnLaunch L;
   int rc = gn_launch_shape(a, &L);
   if (rc) return rc;
@@ -716,6 +744,8 @@ extern "C" int sta_groupnorm_bwd(const sta_groupnorm_args* a, void* stream) {
   GnParams p{};
   p.x = reinterpret_cast<const __half*>(a->x);
   p.dy = reinterpret_cast<const __half*>(a->d_out);
+  p.dres = reinterpret_cast<const __half*>(a->d_res);
+  p.dres_stride = a->d_res_stride > 0 ? a->d_res_stride : a->channels;
   p.out = reinterpret_cast<__half*>(a->out);
   p.xb = reinterpret_cast<const __half*>(a->x_bias);
   p.xb_stride = a->x_bias_stride > 0 ? a->x_bias_stride : a->channels;

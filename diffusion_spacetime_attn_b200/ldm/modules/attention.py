@@ -461,9 +461,11 @@ class SpatialTransformer(nn.Module):
         b, c, h, w = x.shape
         f32 = torch.float32
         nw, nb = cached_sum(self, "gn_w", [self.norm.weight], f32), cached_sum(self, "gn_b", [self.norm.bias], f32)
+        # x feeds the GroupNorm and the `+ x_in` residual: the fork hands both gradients to one GroupNorm backward launch
+        xn, x = ops.group_norm_silu_fork(x, nw, nb, self.norm.eps, False)
+        xn = nhwc_tokens(xn)
         x_in = nhwc_tokens(x)
         x_in = x_in if x_in.is_contiguous() else x_in.contiguous()
-        xn = nhwc_tokens(ops.group_norm_silu(x, nw, nb, self.norm.eps, False))
         w_in = cached_sum(self, "w_in", [self.proj_in.weight], torch.float16).reshape(self.proj_in.out_channels, c)
         w_out = cached_sum(self, "w_out", [self.proj_out.weight], torch.float16).reshape(c, -1)
         with torch.autocast("cuda", enabled=False):

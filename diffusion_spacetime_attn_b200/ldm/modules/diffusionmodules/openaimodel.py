@@ -138,8 +138,9 @@ class ResBlock(TimestepBlock):
         f32, f16 = th.float32, th.float16
         conv1, conv2, emb_lin = self.in_layers[2], self.out_layers[3], self.emb_layers[1]
         n1, n2 = self.in_layers[0], self.out_layers[0]
-        g1 = _ops.group_norm_silu(x, cached_sum(self, "g1", [n1.weight], f32), cached_sum(self, "b1", [n1.bias], f32),
-                                  n1.eps, True)
+        # x feeds the first GroupNorm and the skip branch: the fork hands both gradients to one GroupNorm backward launch
+        g1, x = _ops.group_norm_silu_fork(x, cached_sum(self, "g1", [n1.weight], f32), cached_sum(self, "b1", [n1.bias], f32),
+                                          n1.eps, True)
         with th.autocast("cuda", enabled=False):
             h = F.conv2d(g1, cached_sum(self, "w1", [conv1.weight], f16), None, conv1.stride, conv1.padding)
             # x_bias = emb_layers(emb) + conv1.bias.  UNetModel.forward hands over one [B, sum C] gather from its

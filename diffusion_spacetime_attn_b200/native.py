@@ -93,7 +93,7 @@ class GroupNormArgs(C.Structure):
         ("x", C.c_void_p), ("d_out", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("out", C.c_void_p),
         ("stats", C.c_void_p), ("bwd_stats", C.c_void_p),
         ("batch", C.c_int32), ("hw", C.c_int32), ("channels", C.c_int32), ("silu", C.c_int32), ("eps", C.c_float),
-        ("x_bias", C.c_void_p), ("x_bias_stride", C.c_int64),
+        ("x_bias", C.c_void_p), ("x_bias_stride", C.c_int64), ("d_res", C.c_void_p), ("d_res_stride", C.c_int64),
     ]
 
 

@@ -371,9 +371,20 @@ def groupnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return out, stats, x
 
 
-def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool, x_bias: Optional[torch.Tensor] = None):
+def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool, x_bias: Optional[torch.Tensor] = None,
+                  d_res: Optional[torch.Tensor] = None):
+    """d_x of GroupNorm[+SiLU]; `d_res` (same shape as x) is a second gradient of x that the kernel adds on the fly."""
     b, c, h, w = x.shape
     d_out = _nhwc(d_out if d_out.dtype == torch.float16 else d_out.to(torch.float16))
+    if d_res is not None:
+        if d_res.shape != x.shape:
+            raise RuntimeError(f"groupnorm_bwd: d_res {tuple(d_res.shape)} must match x {tuple(x.shape)}")
+        d_res = d_res if d_res.dtype == torch.float16 else d_res.to(torch.float16)
+        rs = d_res.stride(3) if w > 1 else (d_res.stride(2) if h > 1 else c)  # NHWC row stride: a channel slice keeps it
+        if not (d_res.stride(1) == 1 and rs >= c and rs % 8 == 0 and d_res.data_ptr() % 16 == 0
+                and (h == 1 or w == 1 or d_res.stride(2) == w * rs) and (b == 1 or d_res.stride(0) == h * w * rs)):
+            d_res, rs = _nhwc(d_res), c
+        res_stride = rs
     d_x = torch.empty_like(x, memory_format=torch.channels_last)
     bstats = torch.empty((b, 32, 2), device=x.device, dtype=torch.float32)
     a = native.GroupNormArgs()
@@ -381,6 +392,7 @@ def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool, x_bias: 
     a.stats, a.bwd_stats = stats.data_ptr(), bstats.data_ptr()
     a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
     a.x_bias, a.x_bias_stride = _check_x_bias(x_bias, b, c)
+    a.d_res, a.d_res_stride = (d_res.data_ptr(), res_stride) if d_res is not None else (None, 0)
     with _timed("groupnorm_bwd", (b, h * w, c)):
         native.check(native.load().sta_groupnorm_bwd(C.byref(a), _stream()), "sta_groupnorm_bwd")
     LAUNCHES["groupnorm_bwd"] += 2
@@ -400,6 +412,33 @@ class GroupNormSiLUFn(torch.autograd.Function):
     def backward(ctx, d_out):
         x, gamma, beta, stats, x_bias = ctx.saved_tensors
         return groupnorm_bwd(x, d_out, gamma, beta, stats, ctx.eps, ctx.silu, x_bias), None, None, None, None, None
+
+
+class GroupNormSiLUForkFn(torch.autograd.Function):
+    """(GroupNorm[+SiLU](x), x): the second output is x itself for the residual branch that every ResBlock /
+    SpatialTransformer takes next to its GroupNorm.  Both gradients arrive in ONE backward call, so the kernel adds the
+    residual gradient while it writes d_x instead of autograd launching a separate accumulation pass per block."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, silu):
+        out, stats, x_nhwc = groupnorm_fwd(x, gamma, beta, eps, silu, None)
+        ctx.set_materialize_grads(False)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(x_nhwc, gamma, beta, stats)
+            ctx.eps, ctx.silu = eps, silu
+        return out, x_nhwc.view_as(x_nhwc)
+
+    @staticmethod
+    def backward(ctx, d_out, d_x_res):
+        x, gamma, beta, stats = ctx.saved_tensors
+        if d_out is None:  # only the pass-through output was used
+            return d_x_res, None, None, None, None
+        return groupnorm_bwd(x, d_out, gamma, beta, stats, ctx.eps, ctx.silu, None, d_res=d_x_res), None, None, None, None
+
+
+def group_norm_silu_fork(x, gamma, beta, eps=1e-5, silu=True):
+    """(GroupNorm(32)(x.float()).half() [-> SiLU], x as NHWC memory) — use the second value for the residual branch."""
+    return GroupNormSiLUForkFn.apply(x, gamma, beta, eps, silu)
 
 
 def group_norm_silu(x, gamma, beta, eps=1e-5, silu=True, x_bias=None):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define STA_B200_VERSION 102 /* major*100 + minor */
+#define STA_B200_VERSION 103 /* major*100 + minor */
 
 /* return codes */
 #define STA_OK 0
@@ -176,6 +176,13 @@ typedef struct {
   const void* x_bias;
   int64_t x_bias_stride; /* elements between the rows of x_bias; 0 = channels (dense).  A larger stride lets x_bias be a
                           * column slice of one [batch, sum of channels] table shared by all ResBlocks. */
+  /* backward only, optional fp16 [batch, hw, channels]: a second gradient w.r.t. x that the kernel adds to d_x on the fly.
+   * x feeds the GroupNorm AND a residual branch in every ResBlock / SpatialTransformer (openaimodel.py:275,
+   * attention.py:332-345); this replaces autograd's separate accumulation pass.  NULL = none; may alias out.
+   * d_res_stride: elements between its rows; 0 = channels (dense).  A larger stride lets d_res be a channel slice of a
+   * wider NHWC tensor (the gradient of the decoder's torch.cat, openaimodel.py:731). */
+  const void* d_res;
+  int64_t d_res_stride;
 } sta_groupnorm_args;
 
 int sta_groupnorm_fwd(const sta_groupnorm_args* args, void* stream);

@@ -51,3 +51,57 @@ def test_groupnorm_accepts_nchw_input_and_rejects_bad_channels():
     assert (y.float() - ref).abs().max().item() < 5e-3
     with pytest.raises(RuntimeError, match="multiple of 32"):
         ops.group_norm_silu(torch.randn(1, 48, 4, 4).half().cuda(), torch.ones(48).cuda(), torch.zeros(48).cuda())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("silu", [True, False])
+@pytest.mark.parametrize("shape", [(2, 320, 64, 64), (2, 1280, 16, 16), (2, 960, 64, 64), (1, 1920, 32, 32), (3, 64, 5, 7)],
+                         ids=str)
+def test_groupnorm_fork_adds_the_residual_gradient_in_the_kernel(shape, silu):
+    """group_norm_silu_fork: y = GN(x) and x itself for the residual branch (openaimodel.py:275, attention.py:345); the
+    backward adds the residual gradient inside the GroupNorm kernel (cluster and two-pass paths).  Checked against
+    d/dx [ sum(GN(x) dy) + sum(x dr) ] in fp32 on the CPU; also each output used alone."""
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(c + h + 1)
+    x = (torch.randn(b, c, h, w, generator=g) * 1.5 + 0.3).half()
+    gamma = 1 + 0.1 * torch.randn(c, generator=g)
+    beta = 0.1 * torch.randn(c, generator=g)
+    dy = (torch.randn(b, c, h, w, generator=g) * 0.1).half()
+    dr = (torch.randn(b, c, h, w, generator=g) * 0.1).half()
+    xf = x.float().requires_grad_(True)
+    ref = F.group_norm(xf, 32, gamma, beta, 1e-5)
+    ref = F.silu(ref) if silu else ref
+    ((ref * dy.float()).sum() + (xf * dr.float()).sum()).backward()
+    gref = xf.grad
+    xd = x.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
+    y, xr = ops.group_norm_silu_fork(xd, gamma.cuda(), beta.cuda(), 1e-5, silu)
+    assert torch.equal(xr, xd) and xr.data_ptr() == xd.data_ptr()
+    torch.autograd.backward([y, xr], [dy.cuda(), dr.cuda().to(memory_format=torch.channels_last)])
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    gerr = (xd.grad.float().cpu() - gref).abs()
+    assert (gerr <= 3e-3 * gref.abs().max() + 1e-2 * gref.abs()).all(), f"bwd max err {gerr.max().item():.3e}"
+    # the residual gradient as a channel slice of a wider NHWC tensor (what torch.cat's backward hands over): read in place
+    wide = torch.zeros(b, c + 96, h, w, dtype=torch.float16, device="cuda").to(memory_format=torch.channels_last)
+    wide[:, 32:32 + c] = dr.cuda()
+    copies, real_nhwc = [], ops._nhwc
+    ops._nhwc = lambda t: (copies.append(1) if not t.is_contiguous(memory_format=torch.channels_last) else None, real_nhwc(t))[1]
+    try:
+        _, stats, x_nhwc = ops.groupnorm_fwd(xd.detach(), gamma.cuda(), beta.cuda(), 1e-5, silu)
+        g_strided = ops.groupnorm_bwd(x_nhwc, dy.cuda().to(memory_format=torch.channels_last), gamma.cuda(), beta.cuda(),
+                                      stats, 1e-5, silu, d_res=wide[:, 32:32 + c])
+    finally:
+        ops._nhwc = real_nhwc
+    assert not copies or min(h, w) == 1, "the channel slice was copied instead of being read in place"
+    assert (g_strided.float() - xd.grad.float()).abs().max().item() <= 2e-3 * gref.abs().max().item()
+    # only one of the two outputs used
+    xe = x.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
+    _, xr = ops.group_norm_silu_fork(xe, gamma.cuda(), beta.cuda(), 1e-5, silu)
+    xr.backward(dr.cuda())
+    assert torch.equal(xe.grad, dr.cuda())
+    xe.grad = None
+    y, _ = ops.group_norm_silu_fork(xe, gamma.cuda(), beta.cuda(), 1e-5, silu)
+    y.backward(dy.cuda())
+    xo = x.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
+    ops.group_norm_silu(xo, gamma.cuda(), beta.cuda(), 1e-5, silu).backward(dy.cuda())
+    assert (xe.grad.float() - xo.grad.float()).abs().max().item() <= 2e-3 * gref.abs().max().item()  # two-pass path: atomics
