@@ -402,7 +402,7 @@ class BasicTransformerBlock(nn.Module):
         g2, b2 = ln(self.norm2)
         g3, b3 = ln(self.norm3)
         with torch.autocast("cuda", enabled=False):
-            n1 = ops.layer_norm(x, g1, b1, self.norm1.eps)
+            n1, x = ops.layer_norm_fork(x, g1, b1, self.norm1.eps)  # x: residual stream; one backward launch for both uses
             sa = ops.self_attention_qkv(F.linear(n1, a1._fused_qkv_weight()), a1.heads)
             t = F.linear(sa, w16(a1.to_out[0]))
             x1, n2 = ops.add_layer_norm(t, cached_sum(self, "bo1", [a1.to_out[0].bias], f32), x, g2, b2, self.norm2.eps)

@@ -528,6 +528,28 @@ class LayerNormFn(torch.autograd.Function):
         return add_layernorm_bwd(d_y, None, xs, stats, gamma), None, None, None
 
 
+class LayerNormForkFn(torch.autograd.Function):
+    """(LayerNorm(x), x): the second output is x itself for the residual stream (attention.py:274 `attn1(norm1(x)) + x`);
+    both gradients arrive in one backward call and the LayerNorm kernel adds the residual one (its d_sum input) instead of
+    autograd launching an accumulation pass per transformer block."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        need = ctx.needs_input_grad[0]
+        xs, y, stats = add_layernorm_fwd(x, None, None, gamma, beta, eps, need_stats=need)
+        if need:
+            ctx.save_for_backward(xs, stats, gamma)
+        ctx.set_materialize_grads(False)
+        return y, xs.view_as(xs)
+
+    @staticmethod
+    def backward(ctx, d_y, d_x_res):
+        xs, stats, gamma = ctx.saved_tensors
+        if d_y is None:
+            return d_x_res, None, None, None
+        return add_layernorm_bwd(d_y, d_x_res, xs, stats, gamma), None, None, None
+
+
 class AddLayerNormFn(torch.autograd.Function):
     """(s, y) = (x + bias + residual, LayerNorm(s)): the residual stream and the next sub-layer's input in one pass.
     Backward: ONE kernel gives d_s_total = d_s + LN'(d_y), which is the gradient of both x and residual."""
@@ -566,6 +588,11 @@ class BiasResidualAddFn(torch.autograd.Function):
 
 def layer_norm(x, gamma, beta, eps=1e-5):
     return LayerNormFn.apply(x, gamma, beta, eps)
+
+
+def layer_norm_fork(x, gamma, beta, eps=1e-5):
+    """(LayerNorm(x), x) — use the second value for the residual branch (see LayerNormForkFn)."""
+    return LayerNormForkFn.apply(x, gamma, beta, eps)
 
 
 def add_layer_norm(x, bias, residual, gamma, beta, eps=1e-5):

@@ -89,6 +89,36 @@ def test_add_layernorm_only_one_output_used():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 4096, 320), (2, 64, 1280), (1, 77, 640)], ids=str)
+def test_layernorm_fork_adds_the_residual_gradient_in_the_kernel(shape):
+    """layer_norm_fork: (LayerNorm(x), x) for `attn1(norm1(x)) + x` (attention.py:274); the residual-stream gradient goes
+    through the kernel's d_sum input.  Checked against d/dx [sum(LN(x) dy) + sum(x dr)] in fp32 on the CPU, and each output
+    used alone."""
+    g = torch.Generator().manual_seed(shape[1])
+    c = shape[-1]
+    x = (torch.randn(shape, generator=g) * 1.3 + 0.2).half()
+    gamma, beta = 1 + 0.1 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    dy, dr = (0.1 * torch.randn(shape, generator=g)).half(), (0.1 * torch.randn(shape, generator=g)).half()
+    xf = x.float().requires_grad_(True)
+    ((F.layer_norm(xf, (c,), gamma, beta, 1e-5) * dy.float()).sum() + (xf * dr.float()).sum()).backward()
+    xd = x.cuda().requires_grad_(True)
+    y, xr = ops.layer_norm_fork(xd, gamma.cuda(), beta.cuda(), 1e-5)
+    assert xr.data_ptr() == xd.data_ptr()
+    torch.autograd.backward([y, xr], [dy.cuda(), dr.cuda()])
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    _close(xd.grad, xf.grad, 3e-3 * xf.grad.abs().max().item(), 1e-2, "d_x (both)")
+    xe = x.cuda().requires_grad_(True)
+    ops.layer_norm_fork(xe, gamma.cuda(), beta.cuda(), 1e-5)[1].backward(dr.cuda())
+    assert torch.equal(xe.grad, dr.cuda())
+    xe.grad = None
+    ops.layer_norm_fork(xe, gamma.cuda(), beta.cuda(), 1e-5)[0].backward(dy.cuda())
+    xo = x.cuda().requires_grad_(True)
+    ops.layer_norm(xo, gamma.cuda(), beta.cuda(), 1e-5).backward(dy.cuda())
+    assert torch.equal(xe.grad, xo.grad)
+
+
+@pytest.mark.gpu
 def test_add_layernorm_rejects_bad_shapes():
     x = torch.randn(4, 12).half().cuda()
     with pytest.raises(RuntimeError, match="multiple of 8"):
