@@ -25,7 +25,11 @@ constexpr int kGnMaxThreads = 512;  // vecs * lanes rounded up to a warp; channe
 constexpr int kGnUnroll = 4;        // independent 16-byte loads in flight per thread
 
 struct GnParams {
-  const __half* x;    // [B, HW, C] (NHWC)
+  const __half* x;    // [B, HW, C] (NHWC); with x1: channels [0, c_split) of the (never materialised) concatenation
+  const __half* x1;   // optional [B, HW, C - c_split]: channels [c_split, C) (forward: torch.cat fused into the read)
+  __half* xcat;       // forward only, optional [B, HW, C]: the concatenation, written as a side output
+  __half* out1;       // backward only, optional: dx is split at c_split into out [B, HW, c_split] and out1 [B, HW, C - c_split]
+  int c_split;
   const __half* dy;   // backward only
   const __half* dres; // backward only, optional [B, HW, C]: a second gradient of x (residual branch), added to dx
   long long dres_stride;  // elements between its rows (>= C: it may be a channel slice of a wider NHWC tensor)
@@ -46,6 +50,23 @@ __device__ __forceinline__ float silu_f(float z) { return __fdividef(z, 1.f + __
 __device__ __forceinline__ float dsilu_f(float z) {
   const float s = __fdividef(1.f, 1.f + __expf(-z));
   return s * fmaf(z, 1.f - s, 1.f);
+}
+
+// This thread's 8 channels [ch0, ch0 + 8) of sample b of a [B, HW, C] activation that may live in two tensors split at
+// channel c_split (p1 == nullptr: one dense tensor): pointer to row 0 and the row stride in elements.  c_split is a
+// multiple of 8, so a 16-byte vector never straddles the two.
+template <typename T>
+struct GnCol {
+  T* base;
+  long long rs;
+  __device__ __forceinline__ T* row(int r) const { return base + (long long)r * rs; }
+};
+template <typename T>
+__device__ __forceinline__ GnCol<T> gn_col(T* p0, T* p1, int c_split, int c, int hw, int b, int ch0) {
+  if (!p1) return {p0 + ((long long)b * hw) * c + ch0, (long long)c};
+  if (ch0 < c_split) return {p0 + ((long long)b * hw) * c_split + ch0, (long long)c_split};
+  const int c1 = c - c_split;
+  return {p1 + ((long long)b * hw) * c1 + (ch0 - c_split), (long long)c1};
 }
 
 // thread -> (row lane, 8-channel vector); threads beyond vecs * lanes (warp padding) only help in the reductions
@@ -136,13 +157,13 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(GnParams p) {
     float xb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.xb_stride + m.c0), xb);
     const int r0 = blockIdx.x * p.rows_per_block, r1 = min(p.hw, r0 + p.rows_per_block);
-    const __half* base = p.x + ((long long)b * p.hw) * p.c + m.c0;
+    const GnCol<const __half> src = gn_col(p.x, p.x1, p.c_split, p.c, p.hw, b, m.c0);
     for (int r = r0 + m.lane; r < r1; r += kGnUnroll * m.lanes) {
       uint4 v[kGnUnroll];
 #pragma unroll
       for (int u = 0; u < kGnUnroll; ++u) {
         const int rr = r + u * m.lanes;
-        if (rr < r1) v[u] = *reinterpret_cast<const uint4*>(base + (long long)rr * p.c);
+        if (rr < r1) v[u] = *reinterpret_cast<const uint4*>(src.row(rr));
       }
 #pragma unroll
       for (int u = 0; u < kGnUnroll; ++u) {
@@ -200,18 +221,20 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(GnParams p) {
   }
   const int r0 = blockIdx.x * p.rows_per_block, r1 = min(p.hw, r0 + p.rows_per_block);
   const long long off = ((long long)b * p.hw) * p.c + m.c0;
+  const GnCol<const __half> src = gn_col(p.x, p.x1, p.c_split, p.c, p.hw, b, m.c0);
   for (int r = r0 + m.lane; r < r1; r += kGnUnroll * m.lanes) {
     uint4 v[kGnUnroll];
 #pragma unroll
     for (int u = 0; u < kGnUnroll; ++u) {
       const int rr = r + u * m.lanes;
-      if (rr < r1) v[u] = *reinterpret_cast<const uint4*>(p.x + off + (long long)rr * p.c);
+      if (rr < r1) v[u] = *reinterpret_cast<const uint4*>(src.row(rr));
     }
 #pragma unroll
     for (int u = 0; u < kGnUnroll; ++u) {
       const int rr = r + u * m.lanes;
       if (rr < r1) {
         float f[8];
+        if (p.xcat) *reinterpret_cast<uint4*>(p.xcat + off + (long long)rr * p.c) = v[u];
         unpack8(v[u], f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -289,6 +312,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_apply_kernel(GnParams p)
   }
   const int r0 = blockIdx.x * p.rows_per_block, r1 = min(p.hw, r0 + p.rows_per_block);
   const long long off = ((long long)b * p.hw) * p.c + m.c0;
+  const GnCol<__half> dst = gn_col(p.out, p.out1, p.c_split, p.c, p.hw, b, m.c0);
   constexpr int U = 2;
   for (int r = r0 + m.lane; r < r1; r += U * m.lanes) {
     uint4 vx[U], vd[U], vr[U];
@@ -320,7 +344,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_bwd_apply_kernel(GnParams p)
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] += d[i];
         }
-        *reinterpret_cast<uint4*>(p.out + off + (long long)rr * p.c) = pack8(f);
+        *reinterpret_cast<uint4*>(dst.row(rr)) = pack8(f);
       }
     }
   }
@@ -363,6 +387,10 @@ static int gn_launch_shape(const sta_groupnorm_args* a, GnLaunch* L) {
 // =====================================================================================================================
 struct GnClusterParams {
   const __half* x;
+  const __half* x1;  // see GnParams: split source (forward), concatenation side output (forward), split dx (backward)
+  __half* xcat;
+  __half* out1;
+  int c_split;
   const __half* dy;
   const __half* dres;  // backward only, optional: added to dx (the gradient of x's other consumer)
   long long dres_stride;  // elements between its rows (>= c)
@@ -452,10 +480,18 @@ __global__ void __launch_bounds__(352) gn_cluster_fwd_kernel(GnClusterParams p) 
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (active) {
       if (p.xb) unpack8(*reinterpret_cast<const uint4*>(p.xb + (long long)b * p.xb_stride + ch0), xb);
+      const GnCol<const __half> src = gn_col(p.x, p.x1, p.c_split, p.c, p.hw, b, ch0);
 #pragma unroll
       for (int u = 0; u < R; ++u) {
         const int rr = r0 + lane_row + u * p.lanes;
-        if (rr < r1) v[u] = *reinterpret_cast<const uint4*>(p.x + off + (long long)rr * p.c);
+        if (rr < r1) v[u] = *reinterpret_cast<const uint4*>(src.row(rr));
+      }
+      if (p.xcat) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const int rr = r0 + lane_row + u * p.lanes;
+          if (rr < r1) *reinterpret_cast<uint4*>(p.xcat + off + (long long)rr * p.c) = v[u];
+        }
       }
 #pragma unroll
       for (int u = 0; u < R; ++u) {
@@ -587,6 +623,7 @@ __global__ void __launch_bounds__(640) gn_cluster_bwd_kernel(GnClusterParams p) 
   // dx = rs * (dxhat - m1 - xhat * m2) = dxhat * rs - q - xhat * pm,  q = rs * m1,  pm = rs * m2
   const float q_lo = rs_lo * tot[2 * gl0] * inv_n, pm_lo = rs_lo * tot[2 * gl0 + 1] * inv_n;
   const float q_hi = nb < 8 ? rs_hi * tot[2 * gl0 + 2] * inv_n : 0.f, pm_hi = nb < 8 ? rs_hi * tot[2 * gl0 + 3] * inv_n : 0.f;
+  const GnCol<__half> dst = gn_col(p.out, p.out1, p.c_split, p.c, p.hw, b, ch0);
   uint4 vres[R];
   if (p.dres) {  // all R loads in flight before the first use
 #pragma unroll
@@ -612,7 +649,7 @@ __global__ void __launch_bounds__(640) gn_cluster_bwd_kernel(GnClusterParams p) 
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] += d[i];
       }
-      *reinterpret_cast<uint4*>(p.out + off + (long long)rr * p.c) = pack8(f);
+      *reinterpret_cast<uint4*>(dst.row(rr)) = pack8(f);
     }
   }
 }
@@ -672,6 +709,10 @@ static int gn_cluster(const sta_groupnorm_args* a, bool bwd, cudaStream_t s, boo
   p.xb_stride = a->x_bias_stride > 0 ? a->x_bias_stride : a->channels;
   p.gamma = a->gamma; p.beta = a->beta;
   p.out = reinterpret_cast<__half*>(a->out);
+  p.x1 = bwd ? nullptr : reinterpret_cast<const __half*>(a->x1);
+  p.xcat = bwd ? nullptr : reinterpret_cast<__half*>(a->x_cat);
+  p.out1 = bwd ? reinterpret_cast<__half*>(a->out1) : nullptr;
+  p.c_split = a->c_split;
   p.stats = a->stats; p.bstats = a->bwd_stats;
   p.hw = a->hw; p.c = a->channels; p.cg = cg; p.chunk_c = chunk_c; p.gc = gc; p.vpr = vpr; p.lanes = lanes;
   p.rows_per_cta = rows_per_cta; p.silu = a->silu; p.eps = a->eps;
@@ -706,12 +747,18 @@ extern "C" int sta_groupnorm_fwd(const sta_groupnorm_args* a, void* stream) {
   if (a->x_bias && (a->x_bias_stride < 0 || a->x_bias_stride % 8 || (a->x_bias_stride > 0 && a->x_bias_stride < a->channels) ||
                     (reinterpret_cast<uintptr_t>(a->x_bias) & 15u)))
     return fail(STA_ERR_BAD_ARG, "sta_groupnorm_fwd: x_bias must be 16-byte aligned with a row stride that is 0 or a multiple of 8 >= channels");
+  if ((a->x1 || a->x_cat) && (!a->x1 || a->c_split < 8 || a->c_split >= a->channels || a->c_split % 8 ||
+                              ((reinterpret_cast<uintptr_t>(a->x1) | reinterpret_cast<uintptr_t>(a->x_cat)) & 15u)))
+    return fail(STA_ERR_BAD_ARG, "sta_groupnorm_fwd: a split source needs x1, 16-byte aligned pointers and 8 <= c_split < channels, c_split %% 8 == 0");
   GnLaunch L;
   int rc = gn_launch_shape(a, &L);
   if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   GnParams p{};
   p.x = reinterpret_cast<const __half*>(a->x);
+  p.x1 = reinterpret_cast<const __half*>(a->x1);
+  p.xcat = reinterpret_cast<__half*>(a->x_cat);
+  p.c_split = a->c_split;
   p.out = reinterpret_cast<__half*>(a->out);
   p.xb = reinterpret_cast<const __half*>(a->x_bias);
   p.xb_stride = a->x_bias_stride > 0 ? a->x_bias_stride : a->channels;
@@ -737,6 +784,8 @@ extern "C" int sta_groupnorm_bwd(const sta_groupnorm_args* a, void* stream) {
   if (a->d_res && ((reinterpret_cast<uintptr_t>(a->d_res) & 15u) || a->d_res_stride < 0 || a->d_res_stride % 8 ||
                    (a->d_res_stride > 0 && a->d_res_stride < a->channels)))
     return fail(STA_ERR_BAD_ARG, "sta_groupnorm_bwd: d_res must be 16-byte aligned with a row stride that is 0 or a multiple of 8 >= channels");
+  if (a->out1 && (a->c_split < 8 || a->c_split >= a->channels || a->c_split % 8 || (reinterpret_cast<uintptr_t>(a->out1) & 15u)))
+    return fail(STA_ERR_BAD_ARG, "sta_groupnorm_bwd: a split d_x needs a 16-byte aligned out1 and 8 <= c_split < channels, c_split %% 8 == 0");
   GnLaunch L;
   int rc = gn_launch_shape(a, &L);
   if (rc) return rc;
@@ -747,6 +796,8 @@ extern "C" int sta_groupnorm_bwd(const sta_groupnorm_args* a, void* stream) {
   p.dres = reinterpret_cast<const __half*>(a->d_res);
   p.dres_stride = a->d_res_stride > 0 ? a->d_res_stride : a->channels;
   p.out = reinterpret_cast<__half*>(a->out);
+  p.out1 = reinterpret_cast<__half*>(a->out1);
+  p.c_split = a->c_split;
   p.xb = reinterpret_cast<const __half*>(a->x_bias);
   p.xb_stride = a->x_bias_stride > 0 ? a->x_bias_stride : a->channels;
   p.gamma = a->gamma; p.beta = a->beta; p.stats = a->stats; p.bstats = a->bwd_stats;

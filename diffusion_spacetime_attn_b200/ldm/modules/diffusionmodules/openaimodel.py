@@ -61,9 +61,15 @@ class TimestepBlock(nn.Module):
 
 
 class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
-    def forward(self, x, emb, context=None, time=None, text_index=None, coef=None, bboxs_curr=None):
+    def forward(self, x, emb, context=None, time=None, text_index=None, coef=None, bboxs_curr=None, skip=None):
+        """`skip`: the encoder activation the decoder concatenates to x first (openaimodel.py:731); a leading ResBlock fuses
+        that cat into its first GroupNorm, anything else gets the plain torch.cat."""
+        if skip is not None and not (len(self) and isinstance(self[0], ResBlock)):
+            x, skip = th.cat([x, skip], dim=1), None
         for layer in self:
-            if isinstance(layer, TimestepBlock):
+            if isinstance(layer, ResBlock) and skip is not None:
+                x, skip = layer(x, emb, skip), None
+            elif isinstance(layer, TimestepBlock):
                 x = layer(x, emb)
             elif isinstance(layer, SpatialTransformer):
                 x = layer(x, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
@@ -123,24 +129,30 @@ class ResBlock(TimestepBlock):
         else:
             self.skip_connection = conv_nd(dims, channels, self.out_channels, 1)
 
-    def forward(self, x, emb):
+    def forward(self, x, emb, skip=None):
+        """`skip` (decoder blocks): the block's input is torch.cat([x, skip], dim=1) (openaimodel.py:731)."""
         flag = self.use_checkpoint and x.shape[-1] * x.shape[-2] >= getattr(self, "checkpoint_min_tokens", 0)
-        return checkpoint(self._forward, (x, emb), self.parameters(), flag)
+        return checkpoint(self._forward, (x, emb, skip), self.parameters(), flag)
 
-    def _forward_fused(self, x, emb):
+    def _forward_fused(self, x, emb, skip=None):
         """openaimodel.py:252-275 for a frozen fp16 NHWC ResBlock.  ATen adds a cuDNN convolution's bias as a separate
         broadcast kernel, and `h + emb_out[:, :, None, None]` is another one; here the convolutions run bias-free and
           * conv1's bias + the projected timestep embedding become ONE fp16 [B, C] vector (the embedding GEMM's epilogue
             adds the conv bias) that the second GroupNorm kernel adds on the fly (sta_groupnorm x_bias),
           * conv2's bias (+ the 1x1 skip convolution's bias) and the residual add are one fused pass; the 1x1 skip
             convolution itself is a token GEMM on the NHWC memory."""
-        b, c, hh, ww = x.shape
         f32, f16 = th.float32, th.float16
         conv1, conv2, emb_lin = self.in_layers[2], self.out_layers[3], self.emb_layers[1]
         n1, n2 = self.in_layers[0], self.out_layers[0]
-        # x feeds the first GroupNorm and the skip branch: the fork hands both gradients to one GroupNorm backward launch
-        g1, x = _ops.group_norm_silu_fork(x, cached_sum(self, "g1", [n1.weight], f32), cached_sum(self, "b1", [n1.bias], f32),
-                                          n1.eps, True)
+        gw, gb = cached_sum(self, "g1", [n1.weight], f32), cached_sum(self, "b1", [n1.bias], f32)
+        if skip is None:
+            # x feeds the first GroupNorm and the skip branch: the fork hands both gradients to one GroupNorm backward launch
+            g1, x = _ops.group_norm_silu_fork(x, gw, gb, n1.eps, True)
+        else:
+            # decoder block: the cat of (x, encoder skip) is read in place by the GroupNorm, which also writes the concatenation
+            # for the 1x1 skip convolution; its backward returns the two gradients as dense tensors
+            g1, x = _ops.cat_group_norm_silu(x, skip, gw, gb, n1.eps, True)
+        b, c, hh, ww = x.shape
         with th.autocast("cuda", enabled=False):
             h = F.conv2d(g1, cached_sum(self, "w1", [conv1.weight], f16), None, conv1.stride, conv1.padding)
             # x_bias = emb_layers(emb) + conv1.bias.  UNetModel.forward hands over one [B, sum C] gather from its
@@ -175,9 +187,11 @@ class ResBlock(TimestepBlock):
         return (_fusable(x) and _frozen(self) and (not self.training or self.out_layers[2].p == 0.0)
                 and (isinstance(sk, nn.Identity) or (isinstance(sk, nn.Conv2d) and sk.kernel_size == (1, 1))))
 
-    def _forward(self, x, emb):
+    def _forward(self, x, emb, skip=None):
+        if skip is not None and not (self._fusable_block(x) and _fusable(skip) and x.shape[1] % 8 == 0 and skip.shape[1] % 8 == 0):
+            x, skip = th.cat([x, skip], dim=1), None
         if self._fusable_block(x):
-            return self._forward_fused(x, emb)
+            return self._forward_fused(x, emb, skip)
         fused = _fusable(x)
         h = self.in_layers[2](gn_silu(self.in_layers[0], x)) if fused else self.in_layers(x)
         emb_out = self.emb_layers(_emb_tensor(emb)).type(h.dtype)
@@ -345,9 +359,8 @@ class UNetModel(nn.Module):
             h = module(h, emb, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
             hs.append(h)
         h = self.middle_block(h, emb, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
-        for module in self.output_blocks:
-            h = th.cat([h, hs.pop()], dim=1)
-            h = module(h, emb, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr)
+        for module in self.output_blocks:  # h = cat([h, hs.pop()], dim=1) happens inside the block's first GroupNorm
+            h = module(h, emb, context, time, text_index, coef=coef, bboxs_curr=bboxs_curr, skip=hs.pop())
         if _fusable(h):  # GroupNorm32 works in fp32 either way; skipping the cast only skips two copies
             return self.out[2](gn_silu(self.out[0], h))
         h = h.type(x.dtype)

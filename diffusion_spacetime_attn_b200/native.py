@@ -94,6 +94,7 @@ class GroupNormArgs(C.Structure):
         ("stats", C.c_void_p), ("bwd_stats", C.c_void_p),
         ("batch", C.c_int32), ("hw", C.c_int32), ("channels", C.c_int32), ("silu", C.c_int32), ("eps", C.c_float),
         ("x_bias", C.c_void_p), ("x_bias_stride", C.c_int64), ("d_res", C.c_void_p), ("d_res_stride", C.c_int64),
+        ("x1", C.c_void_p), ("x_cat", C.c_void_p), ("out1", C.c_void_p), ("c_split", C.c_int32),
     ]
 
 

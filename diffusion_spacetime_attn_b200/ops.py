@@ -353,27 +353,38 @@ def _check_x_bias(x_bias, b: int, c: int):
 
 
 def groupnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
-                  x_bias: Optional[torch.Tensor] = None):
+                  x_bias: Optional[torch.Tensor] = None, x1: Optional[torch.Tensor] = None):
+    """(out, stats, x as NHWC memory).  With `x1` the normalised tensor is torch.cat([x, x1], dim=1): the kernel reads the two
+    parts in place and also writes the concatenation, which is returned as the third value."""
     _require(x, "x")
     _require(gamma, "gamma", torch.float32)
     _require(beta, "beta", torch.float32)
     b, c, h, w = x.shape
     x = _nhwc(x)
-    out = torch.empty_like(x, memory_format=torch.channels_last)
-    stats = torch.empty((b, 32, 2), device=x.device, dtype=torch.float32)
     a = native.GroupNormArgs()
+    if x1 is not None:
+        _require(x1, "x1")
+        if x1.shape[0] != b or tuple(x1.shape[2:]) != (h, w):
+            raise RuntimeError(f"groupnorm_fwd: x1 {tuple(x1.shape)} does not concatenate with x {tuple(x.shape)} along channels")
+        x1 = _nhwc(x1)
+        c_split, c = c, c + x1.shape[1]
+        xcat = torch.empty((b, c, h, w), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        a.x1, a.x_cat, a.c_split = x1.data_ptr(), xcat.data_ptr(), c_split
+    out = torch.empty((b, c, h, w), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    stats = torch.empty((b, 32, 2), device=x.device, dtype=torch.float32)
     a.x, a.gamma, a.beta, a.out, a.stats = x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), stats.data_ptr()
     a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
     a.x_bias, a.x_bias_stride = _check_x_bias(x_bias, b, c)
     with _timed("groupnorm_fwd", (b, h * w, c)):
         native.check(native.load().sta_groupnorm_fwd(C.byref(a), _stream()), "sta_groupnorm_fwd")
     LAUNCHES["groupnorm_fwd"] += 2
-    return out, stats, x
+    return out, stats, (x if x1 is None else xcat)
 
 
 def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool, x_bias: Optional[torch.Tensor] = None,
-                  d_res: Optional[torch.Tensor] = None):
-    """d_x of GroupNorm[+SiLU]; `d_res` (same shape as x) is a second gradient of x that the kernel adds on the fly."""
+                  d_res: Optional[torch.Tensor] = None, split: Optional[int] = None):
+    """d_x of GroupNorm[+SiLU]; `d_res` (same shape as x) is a second gradient of x that the kernel adds on the fly.  With
+    `split` the result is written as two dense tensors (d_x[:, :split], d_x[:, split:]) — the gradient of a fused cat."""
     b, c, h, w = x.shape
     d_out = _nhwc(d_out if d_out.dtype == torch.float16 else d_out.to(torch.float16))
     if d_res is not None:
@@ -385,9 +396,14 @@ def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool, x_bias: 
                 and (h == 1 or w == 1 or d_res.stride(2) == w * rs) and (b == 1 or d_res.stride(0) == h * w * rs)):
             d_res, rs = _nhwc(d_res), c
         res_stride = rs
-    d_x = torch.empty_like(x, memory_format=torch.channels_last)
-    bstats = torch.empty((b, 32, 2), device=x.device, dtype=torch.float32)
     a = native.GroupNormArgs()
+    if split is None:
+        d_x = torch.empty_like(x, memory_format=torch.channels_last)
+    else:
+        d_x = torch.empty((b, split, h, w), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        d_x1 = torch.empty((b, c - split, h, w), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+        a.out1, a.c_split = d_x1.data_ptr(), split
+    bstats = torch.empty((b, 32, 2), device=x.device, dtype=torch.float32)
     a.x, a.d_out, a.gamma, a.beta, a.out = x.data_ptr(), d_out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), d_x.data_ptr()
     a.stats, a.bwd_stats = stats.data_ptr(), bstats.data_ptr()
     a.batch, a.hw, a.channels, a.silu, a.eps = b, h * w, c, int(silu), float(eps)
@@ -396,7 +412,7 @@ def groupnorm_bwd(x, d_out, gamma, beta, stats, eps: float, silu: bool, x_bias: 
     with _timed("groupnorm_bwd", (b, h * w, c)):
         native.check(native.load().sta_groupnorm_bwd(C.byref(a), _stream()), "sta_groupnorm_bwd")
     LAUNCHES["groupnorm_bwd"] += 2
-    return d_x
+    return d_x if split is None else (d_x, d_x1)
 
 
 class GroupNormSiLUFn(torch.autograd.Function):
@@ -434,6 +450,39 @@ class GroupNormSiLUForkFn(torch.autograd.Function):
         if d_out is None:  # only the pass-through output was used
             return d_x_res, None, None, None, None
         return groupnorm_bwd(x, d_out, gamma, beta, stats, ctx.eps, ctx.silu, None, d_res=d_x_res), None, None, None, None
+
+
+class CatGroupNormSiLUFn(torch.autograd.Function):
+    """(GroupNorm[+SiLU](cat([h, skip], 1)), cat([h, skip], 1)) in one pass over h and skip (openaimodel.py:731 + :258): the
+    decoder's torch.cat is fused into the first GroupNorm of the ResBlock that consumes it.  Backward: both gradients (of the
+    normalised tensor and of the concatenation, i.e. the ResBlock's skip branch) arrive together, and the kernel writes
+    d_h and d_skip as two DENSE tensors — the stock cat hands out strided channel slices that every consumer has to copy."""
+
+    @staticmethod
+    def forward(ctx, h, skip, gamma, beta, eps, silu):
+        out, stats, xcat = groupnorm_fwd(h, gamma, beta, eps, silu, None, x1=skip)
+        ctx.set_materialize_grads(False)
+        ctx.c_split = h.shape[1]
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ctx.save_for_backward(xcat, gamma, beta, stats)
+            ctx.eps, ctx.silu = eps, silu
+        return out, xcat
+
+    @staticmethod
+    def backward(ctx, d_out, d_cat):
+        xcat, gamma, beta, stats = ctx.saved_tensors
+        c0 = ctx.c_split
+        if d_out is None:
+            if d_cat is None:
+                return None, None, None, None, None, None
+            return d_cat[:, :c0], d_cat[:, c0:], None, None, None, None
+        d_h, d_skip = groupnorm_bwd(xcat, d_out, gamma, beta, stats, ctx.eps, ctx.silu, None, d_res=d_cat, split=c0)
+        return d_h, d_skip, None, None, None, None
+
+
+def cat_group_norm_silu(h, skip, gamma, beta, eps=1e-5, silu=True):
+    """(GroupNorm(32)(cat([h, skip], 1).float()).half() [-> SiLU], cat([h, skip], 1)) without a separate cat kernel."""
+    return CatGroupNormSiLUFn.apply(h, skip, gamma, beta, eps, silu)
 
 
 def group_norm_silu_fork(x, gamma, beta, eps=1e-5, silu=True):

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define STA_B200_VERSION 103 /* major*100 + minor */
+#define STA_B200_VERSION 104 /* major*100 + minor */
 
 /* return codes */
 #define STA_OK 0
@@ -183,6 +183,16 @@ typedef struct {
    * wider NHWC tensor (the gradient of the decoder's torch.cat, openaimodel.py:731). */
   const void* d_res;
   int64_t d_res_stride;
+  /* torch.cat([h, skip], dim=1) of the decoder (openaimodel.py:731) fused into the GroupNorm that consumes it.
+   * Forward: x1 != NULL means x holds channels [0, c_split) as a dense [batch, hw, c_split] tensor and x1 the remaining
+   * channels as [batch, hw, channels - c_split]; x_cat (optional) receives the dense concatenation [batch, hw, channels]
+   * (the ResBlock's skip branch and the backward need it).  Backward: x is that dense concatenation; out1 != NULL splits
+   * d_x the same way (out: [batch, hw, c_split], out1: the rest), so the gradient of the cat is two dense tensors instead
+   * of two strided views.  c_split must be a multiple of 8. */
+  const void* x1;
+  void* x_cat;
+  void* out1;
+  int32_t c_split;
 } sta_groupnorm_args;
 
 int sta_groupnorm_fwd(const sta_groupnorm_args* args, void* stream);

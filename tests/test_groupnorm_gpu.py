@@ -105,3 +105,54 @@ def test_groupnorm_fork_adds_the_residual_gradient_in_the_kernel(shape, silu):
     xo = x.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
     ops.group_norm_silu(xo, gamma.cuda(), beta.cuda(), 1e-5, silu).backward(dy.cuda())
     assert (xe.grad.float() - xo.grad.float()).abs().max().item() <= 2e-3 * gref.abs().max().item()  # two-pass path: atomics
+
+
+# decoder shapes of the SD-v1 UNet at 512^2 (B = 2): (channels of h, channels of the encoder skip, h, w) + an odd one
+CAT_SHAPES = [(1280, 1280, 8, 8), (1280, 640, 16, 16), (640, 320, 32, 32), (640, 320, 64, 64), (320, 320, 64, 64), (40, 24, 5, 7)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", CAT_SHAPES, ids=str)
+def test_cat_groupnorm_reads_the_two_parts_in_place_and_splits_the_gradient(shape):
+    """cat_group_norm_silu(h, skip) == (GN+SiLU(cat([h, skip], 1)), cat([h, skip], 1)) (openaimodel.py:731 + :258), cluster and
+    two-pass kernels.  The concatenation must be exact; the gradient (of sum(GN dy) + sum(cat dr)) comes back as two dense
+    tensors and matches fp32 autograd on the CPU."""
+    c0, c1, h, w = shape
+    g = torch.Generator().manual_seed(c0 + c1 + h)
+    xh = (torch.randn(2, c0, h, w, generator=g) * 1.5 + 0.3).half()
+    xs = (torch.randn(2, c1, h, w, generator=g) * 0.7 - 0.2).half()
+    c = c0 + c1
+    gamma, beta = 1 + 0.1 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g)
+    dy = (torch.randn(2, c, h, w, generator=g) * 0.1).half()
+    dr = (torch.randn(2, c, h, w, generator=g) * 0.1).half()
+    fh, fs = xh.float().requires_grad_(True), xs.float().requires_grad_(True)
+    cat = torch.cat([fh, fs], dim=1)
+    ref = F.silu(F.group_norm(cat, 32, gamma, beta, 1e-5))
+    ((ref * dy.float()).sum() + (cat * dr.float()).sum()).backward()
+    dh = xh.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
+    ds = xs.cuda().to(memory_format=torch.channels_last).requires_grad_(True)
+    y, xc = ops.cat_group_norm_silu(dh, ds, gamma.cuda(), beta.cuda(), 1e-5, True)
+    assert torch.equal(xc, torch.cat([dh, ds], dim=1)), "the side output is not the exact concatenation"
+    err = (y.float().cpu() - ref.detach()).abs()
+    assert (err <= 2e-3 + 4e-3 * ref.detach().abs()).all(), f"fwd max err {err.max().item():.3e}"
+    torch.autograd.backward([y, xc], [dy.cuda(), dr.cuda().to(memory_format=torch.channels_last)])
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    for got, want, name in ((dh.grad, fh.grad, "d_h"), (ds.grad, fs.grad, "d_skip")):
+        assert got.is_contiguous(memory_format=torch.channels_last) or min(h, w) == 1, f"{name} is not dense NHWC"
+        gerr = (got.float().cpu() - want).abs()
+        assert (gerr <= 3e-3 * want.abs().max() + 1e-2 * want.abs()).all(), f"{name} max err {gerr.max().item():.3e}"
+    # only the concatenation used
+    dh.grad = ds.grad = None
+    _, xc = ops.cat_group_norm_silu(dh, ds, gamma.cuda(), beta.cuda(), 1e-5, True)
+    xc.backward(dr.cuda())
+    assert torch.equal(dh.grad, dr.cuda()[:, :c0]) and torch.equal(ds.grad, dr.cuda()[:, c0:])
+
+
+@pytest.mark.gpu
+def test_cat_groupnorm_rejects_bad_splits():
+    gamma, beta = torch.ones(64).cuda(), torch.zeros(64).cuda()
+    with pytest.raises(RuntimeError, match="c_split"):
+        ops.cat_group_norm_silu(torch.randn(1, 60, 4, 4).half().cuda(), torch.randn(1, 4, 4, 4).half().cuda(), gamma, beta)
+    with pytest.raises(RuntimeError, match="concatenate"):
+        ops.cat_group_norm_silu(torch.randn(1, 32, 4, 4).half().cuda(), torch.randn(1, 32, 8, 4).half().cuda(), gamma, beta)
