@@ -509,15 +509,17 @@ __global__ void __launch_bounds__(352) gn_cluster_fwd_kernel(GnClusterParams p) 
     }
     gn_cta_group_sums(gn_smem, red, s, q, active, lane_row, j, p);
   }
+  float sc[8], sh[8], gam[8], bet[8];
+  if (active) {  // issued before the cluster reduction: their L2 latency hides behind its two cluster barriers
+    load8(p.gamma + ch0, gam);
+    load8(p.beta + ch0, bet);
+  }
   gn_cluster_totals(red, tot, 2 * p.gc);
   const int g0 = chunk * p.gc;
   if (blockIdx.x == 0 && (int)threadIdx.x < 2 * p.gc)  // raw sums for the backward (same layout as the two-pass path)
     p.stats[((long long)b * kGnGroups + g0) * 2 + threadIdx.x] = tot[threadIdx.x];
   if (!active) return;
   const float inv_n = 1.f / ((float)p.hw * (float)p.cg);
-  float sc[8], sh[8], gam[8], bet[8];
-  load8(p.gamma + ch0, gam);
-  load8(p.beta + ch0, bet);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int gl = (j * 8 + i) / p.cg;  // group within the chunk
@@ -616,6 +618,16 @@ __global__ void __launch_bounds__(640) gn_cluster_bwd_kernel(GnClusterParams p) 
     }
     gn_cta_group_sums(gn_smem, red, a1, a2, active, lane_row, j, p);
   }
+  // the residual-branch gradient is fetched before the cluster reduction (a second DRAM round trip otherwise); a1 / a2 are
+  // dead here, so the registers are free
+  uint4 vres[R];
+  if (p.dres && active) {
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int rr = r0 + lane_row + u * p.lanes;
+      if (rr < r1) vres[u] = *reinterpret_cast<const uint4*>(p.dres + ((long long)b * p.hw + rr) * p.dres_stride + ch0);
+    }
+  }
   gn_cluster_totals(red, tot, 2 * p.gc);
   if (blockIdx.x == 0 && (int)threadIdx.x < 2 * p.gc && p.bstats)
     p.bstats[((long long)b * kGnGroups + g0) * 2 + threadIdx.x] = tot[threadIdx.x];
@@ -624,14 +636,6 @@ __global__ void __launch_bounds__(640) gn_cluster_bwd_kernel(GnClusterParams p) 
   const float q_lo = rs_lo * tot[2 * gl0] * inv_n, pm_lo = rs_lo * tot[2 * gl0 + 1] * inv_n;
   const float q_hi = nb < 8 ? rs_hi * tot[2 * gl0 + 2] * inv_n : 0.f, pm_hi = nb < 8 ? rs_hi * tot[2 * gl0 + 3] * inv_n : 0.f;
   const GnCol<__half> dst = gn_col(p.out, p.out1, p.c_split, p.c, p.hw, b, ch0);
-  uint4 vres[R];
-  if (p.dres) {  // all R loads in flight before the first use
-#pragma unroll
-    for (int u = 0; u < R; ++u) {
-      const int rr = r0 + lane_row + u * p.lanes;
-      if (rr < r1) vres[u] = *reinterpret_cast<const uint4*>(p.dres + ((long long)b * p.hw + rr) * p.dres_stride + ch0);
-    }
-  }
 #pragma unroll
   for (int u = 0; u < R; ++u) {
     const int rr = r0 + lane_row + u * p.lanes;

@@ -15,6 +15,7 @@
 #include "../../include/sta_b200.h"
 #include "sta_common.cuh"
 #include "sta_host.h"
+#include <stdlib.h>
 
 namespace sta {
 
@@ -70,7 +71,10 @@ __device__ __forceinline__ float row_sum(float v, int tpr) {
 
 // tpr lanes per row (32 / tpr rows per warp); a lane owns vectors sub, sub + tpr, ... (NV of them, the tail predicated
 // off).  SD-v1 widths are 40 * 2^k vectors -> tpr = 8 * 2^k, NV = 5: no idle lanes, 5 independent 16-byte loads in flight.
-template <int NV>
+// PRE: prefetch bias / gamma / beta with the row (latency-bound launches: up to ~2 M elements); without it they are fetched
+// where they are used, which keeps the kernel at 128 registers for the bandwidth-bound shapes (8192 x 320: 4 blocks per SM
+// instead of 2).
+template <int NV, bool PRE>
 __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
   const int tpr = p.tpr, rpw = 32 / tpr;
   const int lane = threadIdx.x & (tpr - 1);
@@ -79,15 +83,28 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
   if (!live) row = p.rows - 1;
   const int vecs = p.c >> 3;
   const long long base = (long long)row * p.c;
-  // phase 1: every load of the row is issued before the first store (sum_out may alias nothing, but the compiler cannot
-  // know: a store between two loads would serialise NV global round trips)
+  // One memory round trip: every load the kernel needs — the row, the residual, the bias, gamma and beta — is issued before
+  // the first use of any of them and before the first store (sum_out may alias nothing, but the compiler cannot know: a store
+  // between two loads would serialise the round trips).  The first version fetched the bias after x had arrived and gamma /
+  // beta after the reductions: three dependent trips, ~1 us of a 5 us kernel.
   uint4 xv[NV], rv[NV];
+  float4 bv[NV][2], gv[NV][2], ev[NV][2];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + tpr * i;
     if (vi < vecs) {
       xv[i] = *reinterpret_cast<const uint4*>(p.x + base + vi * 8);
       if (p.res) rv[i] = *reinterpret_cast<const uint4*>(p.res + base + vi * 8);
+      if (PRE && p.bias) {
+        bv[i][0] = *reinterpret_cast<const float4*>(p.bias + vi * 8);
+        bv[i][1] = *reinterpret_cast<const float4*>(p.bias + vi * 8 + 4);
+      }
+      if (PRE && p.gamma) {
+        gv[i][0] = *reinterpret_cast<const float4*>(p.gamma + vi * 8);
+        gv[i][1] = *reinterpret_cast<const float4*>(p.gamma + vi * 8 + 4);
+        ev[i][0] = *reinterpret_cast<const float4*>(p.beta + vi * 8);
+        ev[i][1] = *reinterpret_cast<const float4*>(p.beta + vi * 8 + 4);
+      }
     }
   }
   float v[NV][8];
@@ -106,8 +123,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
         rounded = false;
       }
       if (p.bias) {
-        float b[8];
-        load8f(p.bias + vi * 8, b);
+        float b[8] = {bv[i][0].x, bv[i][0].y, bv[i][0].z, bv[i][0].w, bv[i][1].x, bv[i][1].y, bv[i][1].z, bv[i][1].w};
+        if (!PRE) load8f(p.bias + vi * 8, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] += b[j];
         rounded = false;
@@ -150,9 +167,13 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(LnParams p) {
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + tpr * i;
     if (vi < vecs && live) {
-      float g[8], b[8], o[8];
-      load8f(p.gamma + vi * 8, g);
-      load8f(p.beta + vi * 8, b);
+      float g[8] = {gv[i][0].x, gv[i][0].y, gv[i][0].z, gv[i][0].w, gv[i][1].x, gv[i][1].y, gv[i][1].z, gv[i][1].w};
+      float b[8] = {ev[i][0].x, ev[i][0].y, ev[i][0].z, ev[i][0].w, ev[i][1].x, ev[i][1].y, ev[i][1].z, ev[i][1].w};
+      if (!PRE) {
+        load8f(p.gamma + vi * 8, g);
+        load8f(p.beta + vi * 8, b);
+      }
+      float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
       *reinterpret_cast<uint4*>(p.y + base + vi * 8) = tk_pack8(o);
@@ -174,13 +195,23 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(LnParams p) {
   const float mean = st.x, rstd = st.y;
   float g[NV][8], xh[NV][8];
   float s1 = 0.f, s2 = 0.f;
+  uint4 dv[NV], xv[NV], sv[NV];  // all loads (the residual-stream gradient too) in flight before the first use
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + tpr * i;
+    if (vi < vecs) {
+      dv[i] = *reinterpret_cast<const uint4*>(p.dy + base + vi * 8);
+      xv[i] = *reinterpret_cast<const uint4*>(p.x + base + vi * 8);
+      if (p.dsum) sv[i] = *reinterpret_cast<const uint4*>(p.dsum + base + vi * 8);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + tpr * i;
     if (vi < vecs) {
       float gam[8];
-      tk_unpack8(*reinterpret_cast<const uint4*>(p.dy + base + vi * 8), g[i]);
-      tk_unpack8(*reinterpret_cast<const uint4*>(p.x + base + vi * 8), xh[i]);
+      tk_unpack8(dv[i], g[i]);
+      tk_unpack8(xv[i], xh[i]);
       load8f(p.gamma + vi * 8, gam);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -203,7 +234,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(LnParams p) {
       for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
       if (p.dsum) {
         float d[8];
-        tk_unpack8(*reinterpret_cast<const uint4*>(p.dsum + base + vi * 8), d);
+        tk_unpack8(sv[i], d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += d[j];
       }
@@ -212,6 +243,18 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(LnParams p) {
   }
 }
 
+
+#define STA_LN_FWD_DISPATCH(PRE, nv, grid, stream, p)                                          \
+  switch (nv) {                                                                                \
+    case 1: add_ln_fwd_kernel<1, PRE><<<grid, kLnWarps * 32, 0, stream>>>(p); break;           \
+    case 2: add_ln_fwd_kernel<2, PRE><<<grid, kLnWarps * 32, 0, stream>>>(p); break;           \
+    case 3: add_ln_fwd_kernel<3, PRE><<<grid, kLnWarps * 32, 0, stream>>>(p); break;           \
+    case 4: add_ln_fwd_kernel<4, PRE><<<grid, kLnWarps * 32, 0, stream>>>(p); break;           \
+    case 5: add_ln_fwd_kernel<5, PRE><<<grid, kLnWarps * 32, 0, stream>>>(p); break;           \
+    case 6: add_ln_fwd_kernel<6, false><<<grid, kLnWarps * 32, 0, stream>>>(p); break;         \
+    case 7: add_ln_fwd_kernel<7, false><<<grid, kLnWarps * 32, 0, stream>>>(p); break;         \
+    default: add_ln_fwd_kernel<8, false><<<grid, kLnWarps * 32, 0, stream>>>(p); break;        \
+  }
 
 #define STA_LN_DISPATCH(kernel, nv, grid, stream, p)                             \
   switch (nv) {                                                                  \
@@ -375,7 +418,12 @@ extern "C" int sta_add_layernorm_fwd(const sta_add_layernorm_args* a, void* stre
   const int rows_per_block = kLnWarps * (32 / p.tpr);
   const unsigned grid = (unsigned)((a->rows + rows_per_block - 1) / rows_per_block);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  STA_LN_DISPATCH(add_ln_fwd_kernel, nv, grid, s, p);
+  static const long long pre_max = getenv("STA_LN_PRE_MAX") ? atoll(getenv("STA_LN_PRE_MAX")) : (2ll << 20);  // A/B knob
+  if ((long long)a->rows * a->channels <= pre_max) {
+    STA_LN_FWD_DISPATCH(true, nv, grid, s, p);
+  } else {
+    STA_LN_FWD_DISPATCH(false, nv, grid, s, p);
+  }
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }
