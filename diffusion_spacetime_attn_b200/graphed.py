@@ -412,4 +412,10 @@ class GraphedDifferentiable:
         if not torch.is_grad_enabled() or not x.requires_grad:
             with torch.no_grad():
                 return self.fn(x)
+        if self.pending:  # a second differentiable call before the first one's backward: its activations are still needed
+            return self.fn(x)
         return _GraphedFn.apply(x, self)
+
+    def reset(self) -> None:
+        """Forget a forward whose backward will never run (its saved activations are simply overwritten by the next call)."""
+        self.pending = False

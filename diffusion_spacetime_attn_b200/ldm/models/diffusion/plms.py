@@ -98,13 +98,14 @@ class PLMSSampler(object):
                      and os.environ.get("STA_GRAPH_DECODE", "1") != "0")
         if not graphable:
             return self._decode_eager(z)
-        key = (tuple(z.shape), z.dtype)
+        amp = torch.is_autocast_enabled()  # the graph replays what the caller's autocast state would have computed eagerly
+        key = (tuple(z.shape), z.dtype, amp)
         g = self._graphed_decode.get(key)
         if g is None:
             from ....graphed import GraphedDifferentiable
 
             def fn(zz):
-                with torch.autocast("cuda", dtype=torch.float16):
+                with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
                     return self._decode_eager(zz)
 
             g = self._graphed_decode[key] = GraphedDifferentiable(fn, z.detach())
@@ -160,8 +161,14 @@ class PLMSSampler(object):
                 old_eps.pop(0)
         return img
 
-    def _loss(self, images, texts, bboxes_pp, names_pp):
-        """plms.py:252-273 per prompt; images [B, 3, Hpx, Wpx] in [0, 1]."""
+    def _loss_weights(self, weights, device):
+        key = (tuple(weights), device)
+        if getattr(self, "_lw_cache", (None, None))[0] != key:
+            self._lw_cache = (key, torch.tensor(weights, dtype=torch.float32, device=device))
+        return self._lw_cache[1]
+
+    def _loss_per_image(self, images, texts, bboxes_pp, names_pp):
+        """plms.py:252-273 literally: one forward_2 / forward_3 call per image."""
         total = images.new_zeros((), dtype=torch.float32)
         per_prompt = []
         for b in range(images.shape[0]):
@@ -176,6 +183,36 @@ class PLMSSampler(object):
                 loss = loss + self.local_loss_weight * self.clip_loss_model.forward_3(crop, "A photo of " + obj).sum()
             per_prompt.append(loss)
             total = total + loss
+        return total, per_prompt
+
+    def _loss(self, images, texts, bboxes_pp, names_pp):
+        """plms.py:252-273 per prompt; images [B, 3, Hpx, Wpx] in [0, 1]."""
+        clip = self.clip_loss_model
+        if not hasattr(clip, "one_minus_cos_batched"):  # a drop-in loss model with only forward_2 / forward_3
+            return self._loss_per_image(images, texts, bboxes_pp, names_pp)
+        # every image of every prompt (the full frame and one crop per object) through the CLIP image tower in ONE pass
+        resized, prompts, weights, first = [], [], [], []
+        for b in range(images.shape[0]):
+            img = images[b].float()
+            size_y, size_x = img.shape[1], img.shape[2]
+            first.append(len(resized))
+            resized.append(clip.resize_global(img))
+            prompts.append(texts[b])
+            weights.append(1.0)
+            for box, name in zip(bboxes_pp[b], names_pp[b]):
+                x1, x2 = max(box[0] - 0.2, 0), min(box[0] + 0.2, 1)
+                y1, y2 = max(box[1] - 0.2, 0), min(box[1] + 0.2, 1)
+                obj = name.lower().replace("the ", "")
+                crop = img[:, int(size_y * y1):int(size_y * y2), int(size_x * x1):int(size_x * x2)]
+                resized.append(clip.resize_crop(crop))
+                prompts.append("A photo of " + obj)
+                weights.append(self.local_loss_weight)
+        first.append(len(resized))
+        terms = clip.one_minus_cos_batched(torch.cat(resized, dim=0), prompts)
+        if any(w != 1.0 for w in weights):
+            terms = terms * self._loss_weights(weights, terms.device)
+        per_prompt = [terms[first[b]:first[b + 1]].sum() for b in range(images.shape[0])]
+        total = per_prompt[0] if len(per_prompt) == 1 else terms.sum()
         return total, per_prompt
 
     def plms_sampling(self, cond, shape, x_T=None, unconditional_guidance_scale=1.0, unconditional_conditioning=None,

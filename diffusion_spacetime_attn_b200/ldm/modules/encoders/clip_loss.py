@@ -139,6 +139,10 @@ class DCLIPLoss(nn.Module):
         self.tokenizer = tokenizer or hash_tokenize
         self._text_cache = {}
         self._resample = {}
+        # CUDA-graph execution (pipeline.py sets it): the image tower's forward-with-grad + backward become one captured graph
+        # pair per number of images (graphed.GraphedDifferentiable; ~1200 eager launches per loss evaluation otherwise)
+        self.graph_encode = False
+        self._graphed_encode = {}
 
     def _text_feat(self, text):
         if text not in self._text_cache:
@@ -147,19 +151,38 @@ class DCLIPLoss(nn.Module):
                 self._text_cache[text] = self.model.encode_text(self.tokenizer([text]).to(dev)).float()
         return self._text_cache[text]
 
+    def _encode_image(self, images_224):
+        if not (self.graph_encode and images_224.is_cuda and images_224.requires_grad and torch.is_grad_enabled()):
+            return self.model.encode_image(images_224)
+        amp = torch.is_autocast_enabled()  # the graph replays what the caller's autocast state would have computed eagerly
+        key = (tuple(images_224.shape), images_224.dtype, amp)
+        g = self._graphed_encode.get(key)
+        if g is None:
+            from ....graphed import GraphedDifferentiable
+
+            def fn(x):
+                with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                    return self.model.encode_image(x)
+
+            g = self._graphed_encode[key] = GraphedDifferentiable(fn, images_224.detach())
+        return g(images_224)
+
     def _one_minus_cos(self, image_224, text):
-        feat = self.model.encode_image(image_224).float()
+        feat = self._encode_image(image_224).float()
         return 1 - F.cosine_similarity(feat, self._text_feat(text))
 
-    def forward_2(self, image, text):
-        """Global loss: image [3, 512, 512] in [0,1] -> 1 - cos(CLIP(img), CLIP(text))   (plms.py:38-45)."""
+    def one_minus_cos_batched(self, images_224, texts):
+        """[K] losses of K already-resized images [K, 3, 224, 224] against K texts: ONE pass through the image tower instead of
+        the reference's K separate batch-1 passes (plms.py:252-273 calls forward_2 / forward_3 per image; the per-image
+        arithmetic is the same, the tower is launch-bound at batch 1)."""
+        feat = self._encode_image(images_224).float()
+        return 1 - F.cosine_similarity(feat, torch.cat([self._text_feat(t) for t in texts], dim=0))
+
+    def resize_global(self, image):
+        """forward_2's resampling of a [3, H, W] image to [1, 3, 224, 224] (plms.py:41)."""
         h, w = image.shape[-2:]
-        # 512 px: Upsample(x7) -> AvgPool2d(16) -> 224 px, the reference's literal pipeline.  Other sizes (the reference
-        # hard-codes 512, SURVEY.md §8a-note) keep the x7 upsample and pool with the window that lands on CLIP's 224 px
-        # (768 px -> window 24); sizes where that is not an integer are resized bilinearly instead.
         if (h * 7) % 224 or (w * 7) % 224:
-            img = F.interpolate(image.unsqueeze(0).float(), size=(224, 224), mode="bilinear", antialias=True, align_corners=False)
-            return self._one_minus_cos(img, text)
+            return F.interpolate(image.unsqueeze(0).float(), size=(224, 224), mode="bilinear", antialias=True, align_corners=False)
         mats = []
         for n in (h, w):
             key = (n, image.device)
@@ -168,9 +191,20 @@ class DCLIPLoss(nn.Module):
             mats.append(self._resample[key])
         with torch.autocast(image.device.type, enabled=False):  # exact fp32, like the reference's pooling of an fp32 image
             small = mats[0] @ image.float() @ mats[1].t()
-        return self._one_minus_cos(small.unsqueeze(0), text)
+        return small.unsqueeze(0)
+
+    @staticmethod
+    def resize_crop(image):
+        """forward_3's bilinear resize of a [3, h, w] crop to [1, 3, 224, 224] (plms.py:31)."""
+        return F.interpolate(image.unsqueeze(0), size=(224, 224), mode="bilinear", antialias=True, align_corners=False)
+
+    def forward_2(self, image, text):
+        """Global loss: image [3, 512, 512] in [0,1] -> 1 - cos(CLIP(img), CLIP(text))   (plms.py:38-45).
+        512 px: Upsample(x7) -> AvgPool2d(16) -> 224 px, the reference's literal pipeline (as two small GEMMs).  Other sizes
+        (the reference hard-codes 512) keep the x7 upsample and pool with the window that lands on CLIP's
+        224 px (768 px -> window 24); sizes where that is not an integer are resized bilinearly instead."""
+        return self._one_minus_cos(self.resize_global(image), text)
 
     def forward_3(self, image, text):
         """Per-object crop loss with a bilinear resize to 224 x 224   (plms.py:29-36)."""
-        img = F.interpolate(image.unsqueeze(0), size=(224, 224), mode="bilinear", antialias=True, align_corners=False)
-        return self._one_minus_cos(img, text)
+        return self._one_minus_cos(self.resize_crop(image), text)

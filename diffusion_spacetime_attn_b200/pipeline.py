@@ -187,6 +187,8 @@ class SpaceTimeAttnPipeline:
             for m in clip.modules():
                 if isinstance(m, torch.nn.LayerNorm):
                     m.float()
+        if cuda_graphs and with_vae:
+            self.clip_loss.graph_encode = True
         cls = DDIMSampler if sampler == "ddim" else PLMSSampler
         self.sampler = cls(self.model, clip_loss_model=self.clip_loss, num_epochs=num_epochs, save_images=save_images,
                            out_dir=out_dir)

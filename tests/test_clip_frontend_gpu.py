@@ -50,3 +50,36 @@ def test_object_crop_loss_matches_the_reference_pipeline_on_gpu():
         (g_out,) = torch.autograd.grad(out.sum(), img)
         assert abs(float(out) - float(ref)) < 1e-5
         assert (g_out - g_ref).abs().max().item() <= 1e-5 * max(1.0, g_ref.abs().max().item()) + 1e-7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("graphed", [False, True], ids=["eager", "graph"])
+def test_batched_loss_equals_the_per_image_loss(graphed):
+    """The sampler sends the full frame and every object crop through the CLIP image tower in ONE pass (and, under CUDA graphs,
+    through a captured forward/backward pair) instead of the reference's one call per image (plms.py:252-273).  fp32 weights:
+    loss and d(loss)/d(image) agree with the literal per-image loop to 1e-4 relative (batch-3 GEMMs round differently from
+    batch-1 GEMMs), for two consecutive images through the same captured graph."""
+    from diffusion_spacetime_attn_b200.ldm.models.diffusion.plms import PLMSSampler
+
+    class _Model:  # the sampler only needs .device and a scheduler-free loss path here
+        device = torch.device("cuda")
+
+    loss = DCLIPLoss(device="cuda", seed=3)
+    loss.graph_encode = graphed
+    sampler = PLMSSampler.__new__(PLMSSampler)
+    sampler.clip_loss_model, sampler.local_loss_weight = loss, 5.0
+    g = torch.Generator().manual_seed(13)
+    boxes, names = [[[0.30, 0.50], [0.70, 0.45]]], [["the red cube", "The blue sphere"]]
+    for _ in range(2):
+        img = torch.rand(1, 3, 512, 512, generator=g).cuda()
+        a, b = img.clone().requires_grad_(True), img.clone().requires_grad_(True)
+        loss.graph_encode = False  # the literal loop, eagerly
+        ref, ref_pp = sampler._loss_per_image(a, ["a red cube left of a blue sphere"], boxes, names)
+        loss.graph_encode = graphed
+        out, out_pp = sampler._loss(b, ["a red cube left of a blue sphere"], boxes, names)
+        ref.backward()
+        out.backward()
+        assert abs(float(out) - float(ref)) <= 1e-4 * abs(float(ref))
+        assert abs(float(out_pp[0]) - float(ref_pp[0])) <= 1e-4 * abs(float(ref))
+        assert (a.grad - b.grad).abs().max().item() <= 1e-3 * a.grad.abs().max().item()
+    assert bool(loss._graphed_encode) == graphed
