@@ -377,6 +377,25 @@ class _GraphedFn(torch.autograd.Function):
         return o.dx.clone(), None
 
 
+def params_fingerprint(module: torch.nn.Module) -> tuple:
+    """(address, version) of every parameter: changes when a weight is re-allocated or rewritten (load_state_dict, .to(),
+    broadcast).  Captured graphs bake the addresses — and whatever caches were derived from the values — in."""
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+def drop_if_weights_changed(owner, attr: str, module: torch.nn.Module, graphs: dict, what: str) -> None:
+    """Clears `graphs` (captured GraphedDifferentiable objects keyed by shape) when `module`'s weights changed since they were
+    captured, so that the next call re-captures instead of replaying stale memory."""
+    fp = params_fingerprint(module)
+    if fp != getattr(owner, attr, None):
+        if graphs:
+            import warnings
+
+            warnings.warn(f"{what} weights changed after CUDA-graph capture: dropping {len(graphs)} captured graph pair(s)")
+            graphs.clear()
+        setattr(owner, attr, fp)
+
+
 class GraphedDifferentiable:
     """`fn`: tensor [shape] -> tensor, frozen weights, fixed shapes.  One call may be in flight at a time (its saved
     activations live in the graph pool until its backward has been replayed) — exactly the sampler's use: decode once per

@@ -98,11 +98,15 @@ class PLMSSampler(object):
                      and os.environ.get("STA_GRAPH_DECODE", "1") != "0")
         if not graphable:
             return self._decode_eager(z)
+        from ....graphed import GraphedDifferentiable, drop_if_weights_changed
+
+        vae = getattr(self.model, "first_stage_model", None)
+        if vae is not None:
+            drop_if_weights_changed(self, "_graphed_decode_fp", vae, self._graphed_decode, "VAE decoder")
         amp = torch.is_autocast_enabled()  # the graph replays what the caller's autocast state would have computed eagerly
         key = (tuple(z.shape), z.dtype, amp)
         g = self._graphed_decode.get(key)
         if g is None:
-            from ....graphed import GraphedDifferentiable
 
             def fn(zz):
                 with torch.autocast("cuda", dtype=torch.float16, enabled=amp):

@@ -154,11 +154,13 @@ class DCLIPLoss(nn.Module):
     def _encode_image(self, images_224):
         if not (self.graph_encode and images_224.is_cuda and images_224.requires_grad and torch.is_grad_enabled()):
             return self.model.encode_image(images_224)
+        from ....graphed import GraphedDifferentiable, drop_if_weights_changed
+
+        drop_if_weights_changed(self, "_graphed_fp", self.model.visual, self._graphed_encode, "CLIP image tower")
         amp = torch.is_autocast_enabled()  # the graph replays what the caller's autocast state would have computed eagerly
         key = (tuple(images_224.shape), images_224.dtype, amp)
         g = self._graphed_encode.get(key)
         if g is None:
-            from ....graphed import GraphedDifferentiable
 
             def fn(x):
                 with torch.autocast("cuda", dtype=torch.float16, enabled=amp):

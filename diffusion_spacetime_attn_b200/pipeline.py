@@ -125,6 +125,8 @@ class SpaceTimeAttnPipeline:
         import os
 
         torch.backends.cudnn.benchmark = os.environ.get("STA_CUDNN_BENCHMARK", "1") == "1"
+        if "STA_CUDNN_BENCHMARK_LIMIT" in os.environ:  # candidates the autotuner times per convolution (torch default 10, 0 = all)
+            torch.backends.cudnn.benchmark_limit = int(os.environ["STA_CUDNN_BENCHMARK_LIMIT"])
         self.device = torch.device(device)
         self.steps, self.scale, self.latent_size = steps, scale, latent_size
         torch.manual_seed(seed)

@@ -83,3 +83,15 @@ def test_batched_loss_equals_the_per_image_loss(graphed):
         assert abs(float(out_pp[0]) - float(ref_pp[0])) <= 1e-4 * abs(float(ref))
         assert (a.grad - b.grad).abs().max().item() <= 1e-3 * a.grad.abs().max().item()
     assert bool(loss._graphed_encode) == graphed
+    if graphed:  # a weight rewritten after the capture: the captured pair is dropped (warning) and re-captured, never replayed stale
+        first = next(iter(loss._graphed_encode.values()))
+        with torch.no_grad():
+            next(loss.model.visual.parameters()).mul_(0.5)
+        a, b = img.clone().requires_grad_(True), img.clone().requires_grad_(True)
+        loss.graph_encode = False
+        ref, _ = sampler._loss_per_image(a, ["a red cube left of a blue sphere"], boxes, names)
+        loss.graph_encode = True
+        with pytest.warns(UserWarning, match="weights changed after CUDA-graph capture"):
+            out, _ = sampler._loss(b, ["a red cube left of a blue sphere"], boxes, names)
+        assert abs(float(out) - float(ref)) <= 1e-4 * abs(float(ref))
+        assert next(iter(loss._graphed_encode.values())) is not first
