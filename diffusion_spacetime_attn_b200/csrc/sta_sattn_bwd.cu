@@ -614,8 +614,8 @@ extern "C" int sta_debug_read(long long* out, int n) {
 
 extern "C" int sta_sattn_bwd(const sta_sattn_bwd_args* a, void* stream) {
   using namespace sta;
-  if (!a || !a->q || !a->k || !a->v || !a->out || !a->d_out || !a->lse || !a->d_q || !a->d_k || !a->d_v ||
-      !a->dq_accum || !a->delta)
+  if (!a || !a->q || !a->k || !a->v || !a->out || !a->d_out || !a->lse || !a->d_q || !a->d_k || !a->d_v || !a->delta ||
+      (!a->dq_accum && a->head_dim != 512))  // the 512-wide path owns every gradient element in one CTA: no fp32 accumulator
     return fail(STA_ERR_BAD_ARG, "sta_sattn_bwd: null pointer");
   if (a->batch < 1 || a->n < 1 || a->heads < 1) return fail(STA_ERR_BAD_ARG, "sta_sattn_bwd: empty shape");
   if ((a->o_token_stride % 8) || (a->o_batch_stride % 8) || (a->do_token_stride % 8) || (a->do_batch_stride % 8) ||
@@ -629,7 +629,8 @@ extern "C" int sta_sattn_bwd(const sta_sattn_bwd_args* a, void* stream) {
     case 40: return launch_sattn_bwd<40>(a, s);
     case 80: return launch_sattn_bwd<80>(a, s);
     case 160: return launch_sattn_bwd<160>(a, s);
+    case 512: return launch_sattn_wide_bwd(a, s);  // KL-VAE mid-block AttnBlock (model.py:150-202)
     default:
-      return fail(STA_ERR_UNSUPPORTED, "sta_sattn_bwd: head_dim %d not built (SD-v1 uses 40/80/160)", a->head_dim);
+      return fail(STA_ERR_UNSUPPORTED, "sta_sattn_bwd: head_dim %d not built (SD-v1 uses 40/80/160, its VAE 512)", a->head_dim);
   }
 }

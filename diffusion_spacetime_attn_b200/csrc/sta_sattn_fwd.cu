@@ -419,7 +419,8 @@ extern "C" int sta_sattn_fwd(const sta_sattn_fwd_args* a, void* stream) {
     case 40: return launch_sattn_fwd<40>(a, s);
     case 80: return launch_sattn_fwd<80>(a, s);
     case 160: return launch_sattn_fwd<160>(a, s);
+    case 512: return launch_sattn_wide_fwd(a, s);  // KL-VAE mid-block AttnBlock (model.py:150-202)
     default:
-      return fail(STA_ERR_UNSUPPORTED, "sta_sattn_fwd: head_dim %d not built (SD-v1 uses 40/80/160)", a->head_dim);
+      return fail(STA_ERR_UNSUPPORTED, "sta_sattn_fwd: head_dim %d not built (SD-v1 uses 40/80/160, its VAE 512)", a->head_dim);
   }
 }

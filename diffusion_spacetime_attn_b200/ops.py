@@ -226,13 +226,14 @@ def sattn_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         d_qkv = d_fused.view(b, n, 3, c).permute(2, 0, 1, 3)  # [3, b, n, c] views, token stride 3c
     else:
         d_qkv = torch.empty((3, b, n, c), device=q.device, dtype=torch.float16)
-    dq_accum = torch.empty((b, n, c), device=q.device, dtype=torch.float32)
+    # head dim 512 (VAE AttnBlock, sta_sattn_wide.cu): every gradient element is owned by one CTA, no fp32 accumulator
+    dq_accum = torch.empty((b, n, c), device=q.device, dtype=torch.float32) if d != 512 else None
     delta = torch.empty((b, heads, n), device=q.device, dtype=torch.float32)
     a = native.SattnBwdArgs()
     a.q, a.k, a.v, a.out, a.d_out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), d_out.data_ptr()
     a.lse = lse.data_ptr()
     a.d_q, a.d_k, a.d_v = d_qkv[0].data_ptr(), d_qkv[1].data_ptr(), d_qkv[2].data_ptr()
-    a.dq_accum, a.delta = dq_accum.data_ptr(), delta.data_ptr()
+    a.dq_accum, a.delta = (dq_accum.data_ptr() if dq_accum is not None else None), delta.data_ptr()
     a.batch, a.n, a.heads, a.head_dim = b, n, heads, d
     a.q_token_stride, a.q_batch_stride = _token_major(q, "q")
     a.k_token_stride, a.k_batch_stride = _token_major(k, "k")
@@ -243,7 +244,7 @@ def sattn_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     a.dqkv_token_stride = 3 * c if d_fused is not None else 0
     with _timed("sattn_bwd", (b, n, heads, d)):
         native.check(native.load().sta_sattn_bwd(C.byref(a), _stream()), "sta_sattn_bwd")
-    LAUNCHES["sattn_bwd"] += 3  # delta, main, dq cast
+    LAUNCHES["sattn_bwd"] += 3  # delta, main, dq cast (head dim 512: delta, key-row pass, query-row pass)
     return d_qkv[0], d_qkv[1], d_qkv[2]
 
 

@@ -1,0 +1,107 @@
+"""GPU parity: the 512-wide flash attention (csrc/sta_sattn_wide.cu, reached through sta_sattn_fwd / sta_sattn_bwd with
+head_dim = 512) against the CPU oracle's attention_core — the core of the KL-VAE mid-block AttnBlock,
+ldm/modules/diffusionmodules/model.py:176-191 (one head of d = C = 512, scale C ** -0.5).
+
+Tolerances as in tests/test_sattn_gpu.py (fp16 storage, fp32 softmax / accumulate): forward |err| <= 2e-3 + 1e-2 |ref|;
+gradients |err| <= 3e-3 max|ref| + 2e-2 |ref| (P and dS are fp16 MMA operands).
+"""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from diffusion_spacetime_attn_b200 import native, ops
+from oracle import sta_oracle as O
+
+# (batch, n, heads): one tile, two tiles, ragged, two heads / two prompts, the 512^2 decode (64 x 64 latent), ragged large
+SHAPES = [(1, 128, 1), (1, 256, 1), (2, 300, 1), (2, 640, 2), (1, 4096, 1), (1, 1100, 1)]
+D = 512
+
+
+def _inputs(b, n, h, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    q = (torch.randn(b, n, h * D, generator=g) * scale).half()
+    k = (torch.randn(b, n, h * D, generator=g) * scale).half()
+    v = torch.randn(b, n, h * D, generator=g).half()
+    return q, k, v
+
+
+def _close(got, ref, atol=2e-3, rtol=1e-2):
+    err = (got.float().cpu() - ref).abs()
+    bad = (err > atol + rtol * ref.abs()).sum().item()
+    assert bad == 0, f"{bad} elements out of tolerance; max abs err {err.max().item():.3e}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
+def test_wide_fwd_matches_oracle(shape):
+    b, n, h = shape
+    q, k, v = _inputs(b, n, h)
+    ref, ref_lse = O.attention_core(q.float(), k.float(), v.float(), h, return_lse=True)
+    out, lse = ops.sattn_fwd(q.cuda(), k.cuda(), v.cuda(), h)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    _close(out, ref)
+    assert (lse.cpu() - ref_lse).abs().max().item() < 2e-3
+
+
+@pytest.mark.gpu
+def test_wide_fwd_large_logits_rescale_path_and_strided_views():
+    """Scores spread over ~+-40 (the running maximum moves by more than 2^8 between key tiles), q/k/v as column slices
+    of one fused [b, n, 3C] projection — the layout AttnBlock hands over."""
+    b, n = 1, 1024
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(b, n, 3 * D, generator=g)
+    qkv[..., : 2 * D] *= 3.0
+    qkv = qkv.half()
+    q, k, v = qkv.chunk(3, dim=-1)
+    ref = O.attention_core(q.float(), k.float(), v.float(), 1)
+    dq, dk, dv = qkv.cuda().chunk(3, dim=-1)
+    out, _ = ops.sattn_fwd(dq, dk, dv, 1)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    _close(out, ref, atol=4e-3, rtol=2e-2)
+
+
+BWD_SHAPES = [(1, 128, 1), (1, 384, 1), (2, 300, 1), (1, 640, 2), (1, 4096, 1)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", BWD_SHAPES, ids=[str(s) for s in BWD_SHAPES])
+def test_wide_bwd_matches_oracle_autograd(shape):
+    b, n, h = shape
+    q, k, v = _inputs(b, n, h, seed=9)
+    g = torch.Generator().manual_seed(10)
+    d_out = (torch.randn(b, n, h * D, generator=g) * 0.1).half()
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = O.attention_core(qf, kf, vf, h)
+    (ref * d_out.float()).sum().backward()
+    dq, dk, dv = q.cuda(), k.cuda(), v.cuda()
+    out, lse = ops.sattn_fwd(dq, dk, dv, h)
+    g_q, g_k, g_v = ops.sattn_bwd(dq, dk, dv, out, lse, d_out.cuda(), h)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    for got, want, nm in ((g_q, qf.grad, "dq"), (g_k, kf.grad, "dk"), (g_v, vf.grad, "dv")):
+        err = (got.float().cpu() - want).abs()
+        bound = 3e-3 * want.abs().max() + 2e-2 * want.abs()
+        bad = (err > bound).sum().item()
+        assert bad == 0, f"{nm}: {bad} elements out of tolerance, max err {err.max().item():.3e} (ref max {want.abs().max().item():.3e})"
+
+
+@pytest.mark.gpu
+def test_wide_bwd_writes_fused_dqkv_buffer():
+    """d_q / d_k / d_v as the three column slices of one [b, n, 3C] gradient (the fused q/k/v 1x1 convolution)."""
+    b, n = 1, 256
+    g = torch.Generator().manual_seed(21)
+    qkv = torch.randn(b, n, 3 * D, generator=g).half().cuda().requires_grad_(True)
+    out = ops.self_attention_qkv(qkv, 1)
+    w = torch.randn(b, n, D, generator=g).cuda()
+    (out.float() * w).sum().backward()
+    q, k, v = (t.detach().float().cpu().requires_grad_(True) for t in qkv.chunk(3, dim=-1))
+    ref = O.attention_core(q, k, v, 1)
+    (ref * w.cpu()).sum().backward()
+    want = torch.cat([q.grad, k.grad, v.grad], dim=-1)
+    torch.cuda.synchronize()
+    assert native.device_error() == 0
+    err = (qkv.grad.float().cpu() - want).abs()
+    assert (err > 3e-3 * want.abs().max() + 2e-2 * want.abs()).sum().item() == 0, f"max err {err.max().item():.3e}"
