@@ -15,14 +15,9 @@
 //           V_j[:, slice] (4 blocks).  S = Q K_j^T (SS) -> online softmax, one thread per row, lazy rescale -> P packed
 //           fp16 in its own TMEM columns -> O += P V_j (TS, two N = 128 MMA groups over adjacent ring slots).
 //           S(j+1) is issued as soon as the softmax warps have READ S(j), so it overlaps the exponentials.
-// backward  ONE kernel template, two roles, CTA = (128-row tile, 128 gradient columns), loop over the other side's tiles t:
-//             role KV (rows = keys j,  X = K_j resident):  S' = K_j Q_t^T, dP' = V_j dO_t^T,
-//                     dV[:, c] += P' dO_t[:, c]   (TS, P' packed fp16 over S')     dK[:, c] += dS' Q_t[:, c]   (SS)
-//             role Q  (rows = queries i, X = Q_i resident): S' = Q_i K_t^T, dP' = dO_i V_t^T,
-//                     dQ[:, c] += dS' K_t[:, c]
-//           with P' = exp2(S' scale log2e - lse_query), dS' = scale P' (dP' - delta_query); dS' goes through a
-//           128B-swizzled smem tile (K-major A operand).  No atomics, no fp32 accumulator in HBM: each gradient element
-//           is owned by one CTA.  Price: S' / dP' are recomputed per column slice and per role.
+// backward  ONE launch, three CTA roles (dK, dQ, dV), CTA = (128-row tile, 256 gradient columns): see the comment above
+//           WideBwdCfg.  No atomics, no fp32 accumulator in HBM: each gradient element is owned by one CTA.  Price: the
+//           scores are recomputed per column slice and per role.
 #include "../../include/sta_b200.h"
 #include "sta_common.cuh"
 #include "sta_host.h"
@@ -288,176 +283,164 @@ sattn_wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 // ------------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------------
+// ONE launch, three CTA roles (blockIdx.y = role x head x column slice); a CTA owns a 128-row tile and 256 gradient columns
+// and loops over the other side's tiles t:
+//   role K (rows = keys j,    X = K_j resident, Y = Q, U = V_j,  W = dO):  S' = K_j Q_t^T, dP' = V_j dO_t^T, dK[:, c] += dS' Q_t[:, c]
+//   role Q (rows = queries i, X = Q_i resident, Y = K, U = dO_i, W = V):   S' = Q_i K_t^T, dP' = dO_i V_t^T, dQ[:, c] += dS' K_t[:, c]
+//   role V (rows = keys j,    X = K_j resident, Y = Q, W = dO):            S' = K_j Q_t^T,                  dV[:, c] += P' dO_t[:, c]
+// P' = exp2(S' scale log2e - lse_query), dS' = scale P' (dP' - delta_query).  dS' goes through a 128B-swizzled smem tile
+// (K-major A operand, SS MMA); P' of role V is packed fp16 over the S' columns (A operand from TMEM, TS MMA) and needs no dP'
+// at all — which is why dV has its own role: it streams 192 KB per tile pair instead of 448 KB.
+// Measured on B200 (N = 4096): the first version (two roles, 128 columns per CTA, two launches) took 415 us and moved
+// 3.6 GB from L2 to the SMs at ~9 TB/s — the kernel is bound by the chip's L2 throughput (~6300 B/clk), not by the tensor
+// pipe, so the lever is bytes streamed per gradient column: 256-column CTAs and the dP'-free dV role cut them by 39 %.
+enum { ROLE_K = 0, ROLE_Q = 1, ROLE_V = 2 };
+
 struct WideBwdCfg {
-  static constexpr int NACC = 128;            // gradient columns per CTA
+  static constexpr int NACC = 256;            // gradient columns per CTA
   static constexpr int NSL = kWD / NACC;
-  static constexpr int RING = 4;              // even (see WideFwdCfg)
-  static constexpr int SMEM = (kWNB + 2 + RING) * kWBlk + 1024;   // X tile, dS' tile (2 blocks), ring
-  static constexpr int TMEM_DP = 128, TMEM_A1 = 256, TMEM_A2 = 384;  // S' [0,128) (P' packed over it)  dP'  acc1  acc2
+  static constexpr int NCB = NACC / 64;       // streamed column-slice blocks per tile
+  static constexpr int RING_DS = 4;           // roles K / Q: X tile (128 KB) + dS' tile (32 KB) + 4 ring blocks
+  static constexpr int RING_V = 6;            // role V: no dS' tile
+  static constexpr int SMEM = (kWNB + 2 + RING_DS) * kWBlk + 1024;
+  static constexpr int TMEM_DP = 128, TMEM_ACC = 256;  // S' [0,128) (role V: P' packed over it)  dP' [128,256)  acc [256,512)
   static constexpr int THREADS = 64 + 128;
 };
+static_assert((kWNB + WideBwdCfg::RING_V) * kWBlk + 1024 <= WideBwdCfg::SMEM, "role V ring");
 
 struct WideBwdParams {
   const float* lse;    // [b, h, n]
   const float* delta;  // [b, h, n]
-  __half* out1;        // role KV: d_v;  role Q: unused
-  __half* out2;        // role KV: d_k;  role Q: d_q      [b, n, h*512] fp16, token stride d_tok
+  __half* d_q;
+  __half* d_k;
+  __half* d_v;         // [b, n, h*512] fp16, token stride d_tok
   long long d_tok;
   int n, heads;
   float scale, scale_log2;
   unsigned int* err;
 };
 
-// tm_x: resident row-side operand (K | Q), tm_y: streamed column-side counterpart (Q | K),
-// tm_u: row-side operand of dP' (V | dO), tm_w: column-side operand of dP' (dO | V)
-template <bool KV>
-__global__ void __launch_bounds__(WideBwdCfg::THREADS, 1)
-sattn_wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
-                      const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_w,
-                      const WideBwdParams p) {
-  using Cfg = WideBwdCfg;
-  constexpr int RING = Cfg::RING, NACC = Cfg::NACC;
+struct WideBwdShared {
+  uint64_t x_full, r_full[WideBwdCfg::RING_V], r_empty[WideBwdCfg::RING_V], sdp_full, pds_ready, acc_full;
+  uint32_t tmem_base;
+  int dead;
+  // statistics of the streamed query tile (roles K / V).  Single-buffered: 224 KB of operand tiles + the alignment slack
+  // leave ~2 KB of the 227 KB for everything static.
+  alignas(16) float lse2[128];  // read four at a time (broadcast float4 loads)
+  alignas(16) float dl[128];
+};
 
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem =
-      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+// tm_x: resident row-side operand, tm_y: streamed column-side counterpart, tm_u / tm_w: row- / column-side operands of dP'
+template <int ROLE>
+__device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared& sh, const CUtensorMap* tm_x,
+                                              const CUtensorMap* tm_y, const CUtensorMap* tm_u, const CUtensorMap* tm_w,
+                                              __half* out, const WideBwdParams& p, int h, int slice) {
+  using Cfg = WideBwdCfg;
+  constexpr bool HAS_DP = ROLE != ROLE_V;      // dP' and dS' are needed
+  constexpr bool COLSTAT = ROLE != ROLE_Q;     // lse / delta belong to the streamed tile's rows (columns of S')
+  constexpr int RING = HAS_DP ? Cfg::RING_DS : Cfg::RING_V;
+  constexpr int NACC = Cfg::NACC;
   unsigned char* sX = smem;
   unsigned char* sDS = sX + kWNB * kWBlk;
-  unsigned char* sR = sDS + 2 * kWBlk;
+  unsigned char* sR = HAS_DP ? sDS + 2 * kWBlk : sDS;
 
-  __shared__ uint64_t x_full, r_full[RING], r_empty[RING], sdp_full, pds_ready, acc_full;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ int dead;
-  // role KV: statistics of the streamed query tile.  Single-buffered (one more named barrier per tile): 224 KB of operand
-  // tiles + the 1 KB alignment slack leave ~2 KB of the 227 KB for everything static.
-  __shared__ __align__(16) float s_lse2[128], s_dl[128];
-
-  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  const int r0 = blockIdx.x * 128, h = blockIdx.y / Cfg::NSL, slice = blockIdx.y % Cfg::NSL, b = blockIdx.z;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 128, b = blockIdx.z;
   const int n = p.n;
   const int T = (n + 127) / 128;
-
-  if (tid == 0) {
-    dead = 0;
-    mbar_init(&x_full, 1);
-    for (int i = 0; i < RING; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 1); }
-    mbar_init(&sdp_full, 1);
-    mbar_init(&pds_ready, 4);
-    mbar_init(&acc_full, 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(&tmem_base_s, 512);
-    tmem_relinquish();
-  }
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_x);
-    tma_prefetch_desc(&tm_y);
-    tma_prefetch_desc(&tm_u);
-    tma_prefetch_desc(&tm_w);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = sh.tmem_base;
+  int* dead = &sh.dead;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    mbar_expect_tx_w(&x_full, kWNB * kWBlk);
-    for (int blk = 0; blk < kWNB; ++blk) tma_load_4d_w(sX + blk * kWBlk, &tm_x, &x_full, blk * 64, h, r0, b);
+    mbar_expect_tx_w(&sh.x_full, kWNB * kWBlk);
+    for (int blk = 0; blk < kWNB; ++blk) tma_load_4d_w(sX + blk * kWBlk, tm_x, &sh.x_full, blk * 64, h, r0, b);
     int idx = 0;
     bool ok = true;
     auto push = [&](const CUtensorMap* tm, int col, int row) {
       const int slot = idx % RING;
-      if (ok) ok = mbar_wait_warp(&r_empty[slot], ((idx / RING) & 1) ^ 1, &dead, p.err, 10);
+      if (ok) ok = mbar_wait_warp(&sh.r_empty[slot], ((idx / RING) & 1) ^ 1, dead, p.err, 10);
       if (ok) {
-        mbar_expect_tx_w(&r_full[slot], kWBlk);
-        tma_load_4d_w(sR + slot * kWBlk, tm, &r_full[slot], col, h, row, b);
+        mbar_expect_tx_w(&sh.r_full[slot], kWBlk);
+        tma_load_4d_w(sR + slot * kWBlk, tm, &sh.r_full[slot], col, h, row, b);
       }
       ++idx;
     };
     for (int t = 0; t < T && ok; ++t) {
-      for (int blk = 0; blk < kWNB; ++blk) push(&tm_y, blk * 64, t * 128);                               // S'
-      for (int blk = 0; blk < kWNB; ++blk) { push(&tm_u, blk * 64, r0); push(&tm_w, blk * 64, t * 128); }  // dP'
-      if (KV)
-        for (int s = 0; s < 2; ++s) push(&tm_w, slice * NACC + s * 64, t * 128);                          // acc1 += P' W_c
-      for (int s = 0; s < 2; ++s) push(&tm_y, slice * NACC + s * 64, t * 128);                            // acc2 += dS' Y_c
+      for (int blk = 0; blk < kWNB; ++blk) push(tm_y, blk * 64, t * 128);                                // S'
+      if (HAS_DP)
+        for (int blk = 0; blk < kWNB; ++blk) { push(tm_u, blk * 64, r0); push(tm_w, blk * 64, t * 128); }  // dP'
+      for (int s = 0; s < Cfg::NCB; ++s)                                                                  // acc += A B_c
+        push(ROLE == ROLE_V ? tm_w : tm_y, slice * NACC + s * 64, t * 128);
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     constexpr uint64_t kdesc_hi = umma_desc_hi_sw128(16, 1024);        // K-major, 128B swizzle
     constexpr uint64_t mndesc_hi = umma_desc_hi_sw128(kWBlk, 1024);    // MN-major, 64-column groups one block apart
     constexpr uint32_t idesc_kk = umma_idesc_f16(128, 128, 0, 0);
-    constexpr uint32_t idesc_acc = umma_idesc_f16(128, NACC, 0, 1);
+    constexpr uint32_t idesc_acc = umma_idesc_f16(128, 128, 0, 1);
     const uint32_t x_addr = smem_u32(sX), ds_addr = smem_u32(sDS), r_addr = smem_u32(sR);
     int cidx = 0;
-    bool ok = mbar_wait_warp(&x_full, 0, &dead, p.err, 20);
+    bool ok = mbar_wait_warp(&sh.x_full, 0, dead, p.err, 20);
     for (int t = 0; t < T && ok; ++t) {
       // S' = X Y_t^T
       for (int blk = 0; blk < kWNB && ok; ++blk) {
         const int slot = cidx % RING;
-        ok = mbar_wait_warp(&r_full[slot], (cidx / RING) & 1, &dead, p.err, 21);
+        ok = mbar_wait_warp(&sh.r_full[slot], (cidx / RING) & 1, dead, p.err, 21);
         if (!ok) break;
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss_w(tmem, umma_desc(kdesc_hi, x_addr + blk * kWBlk + k * 32),
                     umma_desc(kdesc_hi, r_addr + slot * kWBlk + k * 32), idesc_kk, blk > 0 || k > 0);
-        umma_commit_w(&r_empty[slot]);
+        umma_commit_w(&sh.r_empty[slot]);
         ++cidx;
       }
       // dP' = U W_t^T: both operands streamed, (U block, W block) in adjacent slots
-      for (int blk = 0; blk < kWNB && ok; ++blk) {
+      for (int blk = 0; HAS_DP && blk < kWNB && ok; ++blk) {
         const int slot = cidx % RING;  // even
-        ok = mbar_wait_warp(&r_full[slot], (cidx / RING) & 1, &dead, p.err, 22) &&
-             mbar_wait_warp(&r_full[slot + 1], (cidx / RING) & 1, &dead, p.err, 23);
+        ok = mbar_wait_warp(&sh.r_full[slot], (cidx / RING) & 1, dead, p.err, 22) &&
+             mbar_wait_warp(&sh.r_full[slot + 1], (cidx / RING) & 1, dead, p.err, 23);
         if (!ok) break;
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_ss_w(tmem + Cfg::TMEM_DP, umma_desc(kdesc_hi, r_addr + slot * kWBlk + k * 32),
                     umma_desc(kdesc_hi, r_addr + (slot + 1) * kWBlk + k * 32), idesc_kk, blk > 0 || k > 0);
-        umma_commit_w(&r_empty[slot]);
-        umma_commit_w(&r_empty[slot + 1]);
+        umma_commit_w(&sh.r_empty[slot]);
+        umma_commit_w(&sh.r_empty[slot + 1]);
         cidx += 2;
       }
       if (!ok) break;
-      umma_commit_w(&sdp_full);
-      ok = mbar_wait_warp(&pds_ready, t & 1, &dead, p.err, 24);
+      umma_commit_w(&sh.sdp_full);
+      ok = mbar_wait_warp(&sh.pds_ready, t & 1, dead, p.err, 24);
       if (!ok) break;
       tc_fence_after();
-      if (KV) {  // acc1 += P' W_c   (A = P' packed fp16 in TMEM, K = the 128 streamed rows)
-        const int slot = cidx % RING;
-        ok = mbar_wait_warp(&r_full[slot], (cidx / RING) & 1, &dead, p.err, 25) &&
-             mbar_wait_warp(&r_full[slot + 1], (cidx / RING) & 1, &dead, p.err, 26);
+      // acc[:, 128 g .. +128) += A B_c, K = the 128 streamed rows; A = P' (packed fp16 in TMEM, role V) or dS' (smem, K-major:
+      // 64 streamed rows per block); B_c = two adjacent ring blocks, MN-major
+      for (int g = 0; g < Cfg::NCB / 2 && ok; ++g) {
+        const int slot = cidx % RING;  // even
+        ok = mbar_wait_warp(&sh.r_full[slot], (cidx / RING) & 1, dead, p.err, 25) &&
+             mbar_wait_warp(&sh.r_full[slot + 1], (cidx / RING) & 1, dead, p.err, 26);
         if (!ok) break;
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts_w(tmem + Cfg::TMEM_A1, tmem + k * 8, umma_desc(mndesc_hi, r_addr + slot * kWBlk + k * 2048), idesc_acc,
-                    t > 0 || k > 0);
-        umma_commit_w(&r_empty[slot]);
-        umma_commit_w(&r_empty[slot + 1]);
-        cidx += 2;
-      }
-      {  // acc2 += dS' Y_c   (A = dS' in smem, K-major: 64 streamed rows per block)
-        const int slot = cidx % RING;
-        ok = mbar_wait_warp(&r_full[slot], (cidx / RING) & 1, &dead, p.err, 27) &&
-             mbar_wait_warp(&r_full[slot + 1], (cidx / RING) & 1, &dead, p.err, 28);
-        if (!ok) break;
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss_w(tmem + Cfg::TMEM_A2, umma_desc(kdesc_hi, ds_addr + (k / 4) * kWBlk + (k % 4) * 32),
-                    umma_desc(mndesc_hi, r_addr + slot * kWBlk + k * 2048), idesc_acc, t > 0 || k > 0);
-        umma_commit_w(&r_empty[slot]);
-        umma_commit_w(&r_empty[slot + 1]);
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t bdesc = umma_desc(mndesc_hi, r_addr + slot * kWBlk + k * 2048);
+          if (ROLE == ROLE_V)
+            umma_ts_w(tmem + Cfg::TMEM_ACC + g * 128, tmem + k * 8, bdesc, idesc_acc, t > 0 || k > 0);
+          else
+            umma_ss_w(tmem + Cfg::TMEM_ACC + g * 128, umma_desc(kdesc_hi, ds_addr + (k / 4) * kWBlk + (k % 4) * 32), bdesc,
+                      idesc_acc, t > 0 || k > 0);
+        }
+        umma_commit_w(&sh.r_empty[slot]);
+        umma_commit_w(&sh.r_empty[slot + 1]);
         cidx += 2;
       }
       // S'(t+1) is issued behind these MMAs (in-order tensor pipe) and sdp_full(t+1) commits after them: the math warps
       // cannot overwrite P' / dS' of tile t before its consumers have finished.
     }
-    if (ok) umma_commit_w(&acc_full);
+    if (ok) umma_commit_w(&sh.acc_full);
   } else {
     // ===================================== per-row math ======================================
     const int r = ((warp & 3) << 5) + lane;  // row of the resident tile = TMEM lane
@@ -466,23 +449,23 @@ sattn_wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) << 5) << 16);
     const float* lse_bh = p.lse + ((long long)b * p.heads + h) * n;
     const float* delta_bh = p.delta + ((long long)b * p.heads + h) * n;
-    // role Q: the statistics belong to this thread's row; role KV: to the streamed tile's rows (columns of S')
-    const float my_lse2 = (!KV && row_ok) ? -lse_bh[row] * 1.4426950408889634f : -INFINITY;
-    const float my_dl = (!KV && row_ok) ? -delta_bh[row] * p.scale : 0.f;
+    // role Q: the statistics belong to this thread's row; roles K / V: to the streamed tile's rows (columns of S')
+    const float my_lse2 = (!COLSTAT && row_ok) ? -lse_bh[row] * 1.4426950408889634f : -INFINITY;
+    const float my_dl = (!COLSTAT && row_ok) ? -delta_bh[row] * p.scale : 0.f;
     auto load_lse2 = [&](int t) { const int qi = t * 128 + r; return (t < T && qi < n) ? -lse_bh[qi] * 1.4426950408889634f : -INFINITY; };
-    auto load_dl = [&](int t) { const int qi = t * 128 + r; return (t < T && qi < n) ? -delta_bh[qi] * p.scale : 0.f; };
-    float pre_lse2 = KV ? load_lse2(0) : 0.f, pre_dl = KV ? load_dl(0) : 0.f;
+    auto load_dl = [&](int t) { const int qi = t * 128 + r; return (HAS_DP && t < T && qi < n) ? -delta_bh[qi] * p.scale : 0.f; };
+    float pre_lse2 = COLSTAT ? load_lse2(0) : 0.f, pre_dl = COLSTAT ? load_dl(0) : 0.f;
     bool ok = true;
     for (int t = 0; t < T; ++t) {
-      if (KV) {  // stage the streamed tile's statistics for broadcast reads (prefetched one tile ahead)
+      if (COLSTAT) {  // stage the streamed tile's statistics for broadcast reads (prefetched one tile ahead)
         if (t > 0) named_bar_sync(2, 128);  // every thread is done reading the previous tile's statistics
-        s_lse2[r] = pre_lse2;
-        s_dl[r] = pre_dl;
+        sh.lse2[r] = pre_lse2;
+        if (HAS_DP) sh.dl[r] = pre_dl;
         named_bar_sync(1, 128);
         pre_lse2 = load_lse2(t + 1);
         pre_dl = load_dl(t + 1);
       }
-      ok = mbar_wait_warp(&sdp_full, t & 1, &dead, p.err, 30);
+      ok = mbar_wait_warp(&sh.sdp_full, t & 1, dead, p.err, 30);
       if (!ok) break;
       tc_fence_after();
       const int valid = n - t * 128;  // streamed rows (columns of S') that exist
@@ -490,17 +473,19 @@ sattn_wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t s[32], dp[32];
         tmem_ld32(lane_addr + c0, s);
-        tmem_ld32(lane_addr + Cfg::TMEM_DP + c0, dp);
+        if (HAS_DP) tmem_ld32(lane_addr + Cfg::TMEM_DP + c0, dp);
         tmem_ld_wait();
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
           float nlv[4], ndv[4];
-          if (KV) {
-            const float4 nl = *reinterpret_cast<const float4*>(&s_lse2[c0 + q]);
-            const float4 nd = *reinterpret_cast<const float4*>(&s_dl[c0 + q]);
+          if (COLSTAT) {
+            const float4 nl = *reinterpret_cast<const float4*>(&sh.lse2[c0 + q]);
             nlv[0] = nl.x; nlv[1] = nl.y; nlv[2] = nl.z; nlv[3] = nl.w;
-            ndv[0] = nd.x; ndv[1] = nd.y; ndv[2] = nd.z; ndv[3] = nd.w;
+            if (HAS_DP) {
+              const float4 nd = *reinterpret_cast<const float4*>(&sh.dl[c0 + q]);
+              ndv[0] = nd.x; ndv[1] = nd.y; ndv[2] = nd.z; ndv[3] = nd.w;
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) { nlv[e] = my_lse2; ndv[e] = my_dl; }
@@ -509,66 +494,105 @@ sattn_wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             pv[e] = fast_exp2(fmaf(__uint_as_float(s[q + e]), p.scale_log2, nlv[e]));
-            dv[e] = pv[e] * fmaf(__uint_as_float(dp[q + e]), p.scale, ndv[e]);  // scale * P' * (dP' - delta)
-            if (!KV && c0 + q + e >= valid) { pv[e] = 0.f; dv[e] = 0.f; }       // keys past the end of the sequence
+            dv[e] = HAS_DP ? pv[e] * fmaf(__uint_as_float(dp[q + e]), p.scale, ndv[e]) : 0.f;  // scale * P' * (dP' - delta)
+            if (!COLSTAT && c0 + q + e >= valid) { pv[e] = 0.f; dv[e] = 0.f; }  // keys past the end of the sequence
           }
           pk[q >> 1] = pack_half2(pv[0], pv[1]);
           pk[(q >> 1) + 1] = pack_half2(pv[2], pv[3]);
           dk[q >> 1] = pack_half2(dv[0], dv[1]);
           dk[(q >> 1) + 1] = pack_half2(dv[2], dv[3]);
         }
-        if (KV && !row_ok) {  // key rows past the end of the sequence
+        if (COLSTAT && !row_ok) {  // key rows past the end of the sequence
 #pragma unroll
           for (int e = 0; e < 16; ++e) { pk[e] = 0u; dk[e] = 0u; }
         }
-        // P' (packed fp16) over the S' columns this thread has already read: columns [c0/2, c0/2 + 16)
-        if (KV) tmem_st16(lane_addr + (c0 >> 1), pk);
-        // dS' row r, streamed columns [c0, c0 + 32): four 16-byte chunks of block c0 / 64
-        unsigned char* ds_blk = sDS + (c0 >> 6) * kWBlk;
-        const int chunk0 = (c0 & 63) >> 3;
+        if (ROLE == ROLE_V) {
+          // P' (packed fp16) over the S' columns this thread has already read: columns [c0/2, c0/2 + 16)
+          tmem_st16(lane_addr + (c0 >> 1), pk);
+        } else {
+          // dS' row r, streamed columns [c0, c0 + 32): four 16-byte chunks of block c0 / 64
+          unsigned char* ds_blk = sDS + (c0 >> 6) * kWBlk;
+          const int chunk0 = (c0 & 63) >> 3;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          *reinterpret_cast<uint4*>(ds_blk + sw128_offset(r, chunk0 + cc)) =
-              make_uint4(dk[4 * cc], dk[4 * cc + 1], dk[4 * cc + 2], dk[4 * cc + 3]);
+          for (int cc = 0; cc < 4; ++cc)
+            *reinterpret_cast<uint4*>(ds_blk + sw128_offset(r, chunk0 + cc)) =
+                make_uint4(dk[4 * cc], dk[4 * cc + 1], dk[4 * cc + 2], dk[4 * cc + 3]);
+        }
       }
-      if (KV) tmem_st_wait();
-      fence_proxy_async_smem();
+      if (ROLE == ROLE_V) tmem_st_wait();
+      else fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pds_ready);
+      if (lane == 0) mbar_arrive(&sh.pds_ready);
     }
     // -------- epilogue: this row's gradient columns [slice * NACC, +NACC) --------
     ok = __all_sync(0xffffffffu, ok);
-    if (ok) ok = mbar_wait_warp(&acc_full, 0, &dead, p.err, 31);
+    if (ok) ok = mbar_wait_warp(&sh.acc_full, 0, dead, p.err, 31);
     if (ok) {
       tc_fence_after();
-      const long long off = ((long long)b * n + row) * p.d_tok + h * kWD + slice * NACC;
+      __half* orow = out + ((long long)b * n + row) * p.d_tok + h * kWD + slice * NACC;
       for (int cc = 0; cc < NACC; cc += 8) {
-        uint32_t a2[8], a1[8];
-        tmem_ld8(lane_addr + Cfg::TMEM_A2 + cc, a2);
-        if (KV) tmem_ld8(lane_addr + Cfg::TMEM_A1 + cc, a1);
+        uint32_t a[8];
+        tmem_ld8(lane_addr + Cfg::TMEM_ACC + cc, a);
         tmem_ld_wait();
         if (row_ok) {
           uint4 v;
-          v.x = pack_half2(__uint_as_float(a2[0]), __uint_as_float(a2[1]));
-          v.y = pack_half2(__uint_as_float(a2[2]), __uint_as_float(a2[3]));
-          v.z = pack_half2(__uint_as_float(a2[4]), __uint_as_float(a2[5]));
-          v.w = pack_half2(__uint_as_float(a2[6]), __uint_as_float(a2[7]));
-          *reinterpret_cast<uint4*>(p.out2 + off + cc) = v;
-          if (KV) {
-            v.x = pack_half2(__uint_as_float(a1[0]), __uint_as_float(a1[1]));
-            v.y = pack_half2(__uint_as_float(a1[2]), __uint_as_float(a1[3]));
-            v.z = pack_half2(__uint_as_float(a1[4]), __uint_as_float(a1[5]));
-            v.w = pack_half2(__uint_as_float(a1[6]), __uint_as_float(a1[7]));
-            *reinterpret_cast<uint4*>(p.out1 + off + cc) = v;
-          }
+          v.x = pack_half2(__uint_as_float(a[0]), __uint_as_float(a[1]));
+          v.y = pack_half2(__uint_as_float(a[2]), __uint_as_float(a[3]));
+          v.z = pack_half2(__uint_as_float(a[4]), __uint_as_float(a[5]));
+          v.w = pack_half2(__uint_as_float(a[6]), __uint_as_float(a[7]));
+          *reinterpret_cast<uint4*>(orow + cc) = v;
         }
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(WideBwdCfg::THREADS, 1)
+sattn_wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                      const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                      const WideBwdParams p) {
+  using Cfg = WideBwdCfg;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem =
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(16) WideBwdShared sh;
+
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  // the two heavy roles first: the light dV CTAs (192 instead of 448 KB streamed per tile pair) fill the tail of the grid
+  const int per_role = p.heads * Cfg::NSL;
+  const int role = blockIdx.y / per_role, h = (blockIdx.y % per_role) / Cfg::NSL, slice = blockIdx.y % Cfg::NSL;
+
+  if (threadIdx.x == 0) {
+    sh.dead = 0;
+    mbar_init(&sh.x_full, 1);
+    for (int i = 0; i < Cfg::RING_V; ++i) { mbar_init(&sh.r_full[i], 1); mbar_init(&sh.r_empty[i], 1); }
+    mbar_init(&sh.sdp_full, 1);
+    mbar_init(&sh.pds_ready, 4);
+    mbar_init(&sh.acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&sh.tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  tc_fence_after();
+
+  if (role == ROLE_K) wide_bwd_body<ROLE_K>(smem, sh, &tm_k, &tm_q, &tm_v, &tm_do, p.d_k, p, h, slice);
+  else if (role == ROLE_Q) wide_bwd_body<ROLE_Q>(smem, sh, &tm_q, &tm_k, &tm_do, &tm_v, p.d_q, p, h, slice);
+  else wide_bwd_body<ROLE_V>(smem, sh, &tm_k, &tm_q, nullptr, &tm_do, p.d_v, p, h, slice);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(sh.tmem_base, 512);
 }
 
 // delta[b,h,i] = <dO[b,i,h,:], O[b,i,h,:]> over the 512 columns of a head: one warp per (b, i, h), two 16-byte vectors of O
@@ -661,31 +685,22 @@ int launch_sattn_wide_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   WideBwdParams p;
   p.lse = a->lse;
   p.delta = a->delta;
+  p.d_q = reinterpret_cast<__half*>(a->d_q);
+  p.d_k = reinterpret_cast<__half*>(a->d_k);
+  p.d_v = reinterpret_cast<__half*>(a->d_v);
   p.d_tok = a->dqkv_token_stride > 0 ? a->dqkv_token_stride : (long long)a->heads * kWD;
   p.n = a->n;
   p.heads = a->heads;
   p.scale = a->scale;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.err = device_error_word();
-  static PerDeviceOnce attr_kv, attr_q;
-  if ((rc = attr_kv.run([] {
-        return cudaFuncSetAttribute(sattn_wide_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  static PerDeviceOnce smem_attr;
+  if ((rc = smem_attr.run([] {
+        return cudaFuncSetAttribute(sattn_wide_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
       })))
     return rc;
-  if ((rc = attr_q.run([] {
-        return cudaFuncSetAttribute(sattn_wide_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-      })))
-    return rc;
-  dim3 grid((a->n + 127) / 128, a->heads * Cfg::NSL, a->batch);
-  // role KV: rows = keys.  X = K, Y = Q, U = V, W = dO
-  p.out1 = reinterpret_cast<__half*>(a->d_v);
-  p.out2 = reinterpret_cast<__half*>(a->d_k);
-  sattn_wide_bwd_kernel<true><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tm_k, tm_q, tm_v, tm_do, p);
-  STA_CUDA_CHECK(cudaGetLastError());
-  // role Q: rows = queries.  X = Q, Y = K, U = dO, W = V
-  p.out1 = nullptr;
-  p.out2 = reinterpret_cast<__half*>(a->d_q);
-  sattn_wide_bwd_kernel<false><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tm_q, tm_k, tm_do, tm_v, p);
+  dim3 grid((a->n + 127) / 128, 3 * a->heads * Cfg::NSL, a->batch);  // roles K, Q, V
+  sattn_wide_bwd_kernel<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tm_q, tm_k, tm_v, tm_do, p);
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }

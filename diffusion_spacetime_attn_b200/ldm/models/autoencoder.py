@@ -12,11 +12,15 @@ between them runs on this package's streaming kernels, NHWC end to end:
   * conv1's bias rides in the second GroupNorm (x_bias), conv2's bias (+ the 1x1 shortcut's) and the residual add are
     one pass (sta_add_layernorm_fwd without a norm) — ATen adds a cuDNN conv bias as a separate broadcast kernel;
   * the 1x1 convolutions (shortcut, attention q/k/v/proj_out) are token GEMMs on the NHWC memory; q/k/v are ONE GEMM.
-The single mid-block attention (1 head, d = 512, N = 4096) is bmm / softmax / bmm as in the reference (model.py:176-191) on
-the fused path, torch SDPA on the plain path.  On CPU / fp32 tensors the plain torch path below runs
+  * the single mid-block attention (1 head, d = 512, N = 4096) is the 512-wide flash kernel (csrc/sta_sattn_wide.cu through
+    sta_sattn_fwd / _bwd): no [N, N] score matrix, which the reference materialises three times (model.py:176-191);
+    STA_VAE_ATTN=materialised selects bmm / softmax / bmm on cuBLAS (the A/B arm of tools/bench_wide.py); torch SDPA on
+    the plain path.  On CPU / fp32 tensors the plain torch path below runs
 (that is what tests/test_vae_golden.py checks against the reference's output on CPU).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn as nn
@@ -127,13 +131,20 @@ class AttnBlock(nn.Module):
                     wq, bq = prev[1], prev[2]
                 slot["qkv"] = (key, wq, bq)
             _, wq, bq = slot["qkv"]
-            q, k, v = F.linear(t, wq, bq).chunk(3, dim=-1)  # [b, hw, c] views
-            # One head of d = 512: torch's SDPA falls back to an sm80 memory-efficient kernel here (3.1 ms backward on
-            # B200, 28 TFLOP/s).  The 4096^2 score matrix is 32 MB in fp16 — the reference materialises it as well
-            # (model.py:176-191) — so this is bmm / softmax / bmm on cuBLAS, fp32 softmax as under autocast.
-            w_ = torch.bmm(q, k.transpose(1, 2))
-            w_ = torch.softmax(w_.float() * (int(c) ** -0.5), dim=2).to(f16)
-            o = torch.bmm(w_, v)
+            qkv = F.linear(t, wq, bq)  # [b, hw, 3c]: q / k / v are its column slices
+            if c == 512 and os.environ.get("STA_VAE_ATTN", "flash") != "materialised":
+                # One head of d = C = 512 (SD-v1's KL-VAE): the 512-wide flash kernel (csrc/sta_sattn_wide.cu) — no [hw, hw]
+                # score matrix (model.py:176-191 writes it three times: bmm output, scaled copy, softmax), and d(qkv) comes
+                # back as ONE [b, hw, 3c] gradient.  B200, 64 x 64 latent: forward 87 us (bmm / softmax / bmm on cuBLAS:
+                # 159 us), forward + backward 397 us (398 us); two 96 x 96 latents: 2.74 ms (3.61 ms).
+                o = ops.self_attention_qkv(qkv, 1)
+            else:
+                # other widths: bmm / softmax / bmm on cuBLAS with the materialised score matrix, fp32 softmax as the
+                # reference computes it under autocast (torch's SDPA has only an sm80 kernel for one wide head)
+                q, k, v = qkv.chunk(3, dim=-1)
+                w_ = torch.bmm(q, k.transpose(1, 2))
+                w_ = torch.softmax(w_.float() * (int(c) ** -0.5), dim=2).to(f16)
+                o = torch.bmm(w_, v)
             o = F.linear(o, cached_sum(self, "wo", [self.proj_out.weight], f16).reshape(c, c))
             x_tok = nhwc_tokens(x)
             x_tok = x_tok if x_tok.is_contiguous() else x_tok.contiguous()

@@ -244,7 +244,7 @@ def sattn_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     a.dqkv_token_stride = 3 * c if d_fused is not None else 0
     with _timed("sattn_bwd", (b, n, heads, d)):
         native.check(native.load().sta_sattn_bwd(C.byref(a), _stream()), "sta_sattn_bwd")
-    LAUNCHES["sattn_bwd"] += 3  # delta, main, dq cast (head dim 512: delta, key-row pass, query-row pass)
+    LAUNCHES["sattn_bwd"] += 3 if d != 512 else 2  # delta, main, dq cast (head dim 512: delta, three-role main)
     return d_qkv[0], d_qkv[1], d_qkv[2]
 
 

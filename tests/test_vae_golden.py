@@ -57,7 +57,7 @@ def test_decoder_fused_fp16_path_matches_reference():
         if isinstance(m, torch.nn.GroupNorm):
             m.float()
     dec.to(memory_format=torch.channels_last)
-    before = ops.launch_count()
+    before, attn_before = ops.launch_count(), (ops.LAUNCHES["sattn_fwd"], ops.LAUNCHES["sattn_bwd"])
     zd = z.cuda().requires_grad_(True)
     with torch.autocast("cuda", dtype=torch.float16):
         img = dec(zd)
@@ -65,8 +65,38 @@ def test_decoder_fused_fp16_path_matches_reference():
     torch.cuda.synchronize()
     assert native.device_error() == 0
     assert ops.launch_count() - before > 100, "the fused kernels did not run"
+    # the mid-block AttnBlock (model.py:150-202, one head of d = 512) went through the 512-wide flash kernel, both ways
+    assert (ops.LAUNCHES["sattn_fwd"], ops.LAUNCHES["sattn_bwd"]) == (attn_before[0] + 1, attn_before[1] + 2)
     e_img, e_dz = _rel(img, img_ref), _rel(zd.grad, dz_ref)
     assert e_img < 5e-3 and e_dz < 2e-2, (e_img, e_dz)
+
+
+@pytest.mark.gpu
+def test_decoder_flash_attention_agrees_with_the_materialised_formulation(monkeypatch):
+    """A/B of the mid-block attention inside the whole decoder: 512-wide flash kernel vs bmm / softmax / bmm with the [N, N]
+    score matrix in HBM (what model.py:176-191 does) — same image and latent gradient to fp16 rounding."""
+    from diffusion_spacetime_attn_b200 import native, ops
+
+    dec, z, G, _, _ = _decoder_and_inputs()
+    dec = dec.cuda().half().requires_grad_(False)
+    for m in dec.modules():
+        if isinstance(m, torch.nn.GroupNorm):
+            m.float()
+    dec.to(memory_format=torch.channels_last)
+    res = {}
+    for arm in ("flash", "materialised"):
+        monkeypatch.setenv("STA_VAE_ATTN", arm)
+        n0 = ops.LAUNCHES["sattn_fwd"]
+        zd = z.cuda().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            img = dec(zd)
+            (img.float() * G.cuda()).sum().backward()
+        torch.cuda.synchronize()
+        assert ops.LAUNCHES["sattn_fwd"] - n0 == (1 if arm == "flash" else 0)
+        res[arm] = (img.detach().float().cpu(), zd.grad.float().cpu())
+    assert native.device_error() == 0
+    assert _rel(res["flash"][0], res["materialised"][0]) < 2e-3
+    assert _rel(res["flash"][1], res["materialised"][1]) < 1e-2
 
 
 @pytest.mark.gpu
