@@ -321,7 +321,8 @@ struct WideBwdParams {
 };
 
 struct WideBwdShared {
-  uint64_t x_full, r_full[WideBwdCfg::RING_V], r_empty[WideBwdCfg::RING_V], sdp_full, pds_ready, acc_full;
+  uint64_t x_full, r_full[WideBwdCfg::RING_V], r_empty[WideBwdCfg::RING_V];
+  uint64_t s_full[2], s_consumed, dp_full, pds_ready, acc_done, acc_full;
   uint32_t tmem_base;
   int dead;
   // statistics of the streamed query tile (roles K / V).  Single-buffered: 224 KB of operand tiles + the alignment slack
@@ -330,6 +331,13 @@ struct WideBwdShared {
   alignas(16) float dl[128];
 };
 
+// Software pipeline (the first version ran  S', dP' -> math -> acc  strictly in sequence: 310 us at N = 4096, the ring idle
+// during the math and the math idle during the MMAs):
+//   roles K / Q   tensor pipe:  dP'(t) | S'(t+1) | acc(t) | dP'(t+1) ...      (ring blocks in exactly this order)
+//                 math warps:   pass 1 (t): P' = exp2(S' ..) kept packed in registers, S' released   — runs under dP'(t)
+//                               pass 2 (t): dS' = P' (scale dP' - delta) -> smem                      — runs under S'(t+1)
+//   role V        S' is double-buffered in TMEM (columns [0,128) / [128,256), P' packed over its own S'):
+//                 tensor pipe:  S'(t+1) | acc(t) ...      math: P'(t) while S'(t+1) streams
 // tm_x: resident row-side operand, tm_y: streamed column-side counterpart, tm_u / tm_w: row- / column-side operands of dP'
 template <int ROLE>
 __device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared& sh, const CUtensorMap* tm_x,
@@ -366,11 +374,13 @@ __device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared
       }
       ++idx;
     };
+    for (int blk = 0; blk < kWNB; ++blk) push(tm_y, blk * 64, 0);                                         // S'(0)
     for (int t = 0; t < T && ok; ++t) {
-      for (int blk = 0; blk < kWNB; ++blk) push(tm_y, blk * 64, t * 128);                                // S'
       if (HAS_DP)
-        for (int blk = 0; blk < kWNB; ++blk) { push(tm_u, blk * 64, r0); push(tm_w, blk * 64, t * 128); }  // dP'
-      for (int s = 0; s < Cfg::NCB; ++s)                                                                  // acc += A B_c
+        for (int blk = 0; blk < kWNB; ++blk) { push(tm_u, blk * 64, r0); push(tm_w, blk * 64, t * 128); }  // dP'(t)
+      if (t + 1 < T)
+        for (int blk = 0; blk < kWNB; ++blk) push(tm_y, blk * 64, (t + 1) * 128);                          // S'(t+1)
+      for (int s = 0; s < Cfg::NCB; ++s)                                                                  // acc(t) += A B_c
         push(ROLE == ROLE_V ? tm_w : tm_y, slice * NACC + s * 64, t * 128);
     }
   } else if (warp == 1) {
@@ -382,8 +392,7 @@ __device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared
     const uint32_t x_addr = smem_u32(sX), ds_addr = smem_u32(sDS), r_addr = smem_u32(sR);
     int cidx = 0;
     bool ok = mbar_wait_warp(&sh.x_full, 0, dead, p.err, 20);
-    for (int t = 0; t < T && ok; ++t) {
-      // S' = X Y_t^T
+    auto issue_s = [&](int buf) {  // S' = X Y^T into TMEM columns [128 buf, +128)
       for (int blk = 0; blk < kWNB && ok; ++blk) {
         const int slot = cidx % RING;
         ok = mbar_wait_warp(&sh.r_full[slot], (cidx / RING) & 1, dead, p.err, 21);
@@ -391,13 +400,15 @@ __device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_ss_w(tmem, umma_desc(kdesc_hi, x_addr + blk * kWBlk + k * 32),
+          umma_ss_w(tmem + buf * 128, umma_desc(kdesc_hi, x_addr + blk * kWBlk + k * 32),
                     umma_desc(kdesc_hi, r_addr + slot * kWBlk + k * 32), idesc_kk, blk > 0 || k > 0);
         umma_commit_w(&sh.r_empty[slot]);
         ++cidx;
       }
-      // dP' = U W_t^T: both operands streamed, (U block, W block) in adjacent slots
-      for (int blk = 0; HAS_DP && blk < kWNB && ok; ++blk) {
+      if (ok) umma_commit_w(&sh.s_full[buf]);
+    };
+    auto issue_dp = [&]() {  // dP' = U W^T: both operands streamed, (U block, W block) in adjacent slots
+      for (int blk = 0; blk < kWNB && ok; ++blk) {
         const int slot = cidx % RING;  // even
         ok = mbar_wait_warp(&sh.r_full[slot], (cidx / RING) & 1, dead, p.err, 22) &&
              mbar_wait_warp(&sh.r_full[slot + 1], (cidx / RING) & 1, dead, p.err, 23);
@@ -411,13 +422,11 @@ __device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared
         umma_commit_w(&sh.r_empty[slot + 1]);
         cidx += 2;
       }
-      if (!ok) break;
-      umma_commit_w(&sh.sdp_full);
-      ok = mbar_wait_warp(&sh.pds_ready, t & 1, dead, p.err, 24);
-      if (!ok) break;
-      tc_fence_after();
-      // acc[:, 128 g .. +128) += A B_c, K = the 128 streamed rows; A = P' (packed fp16 in TMEM, role V) or dS' (smem, K-major:
-      // 64 streamed rows per block); B_c = two adjacent ring blocks, MN-major
+      if (ok) umma_commit_w(&sh.dp_full);
+    };
+    // acc[:, 128 g .. +128) += A B_c, K = the 128 streamed rows; A = P' (packed fp16 in TMEM over S' buffer t & 1, role V) or
+    // dS' (smem, K-major: 64 streamed rows per block); B_c = two adjacent ring blocks, MN-major
+    auto issue_acc = [&](int t) {
       for (int g = 0; g < Cfg::NCB / 2 && ok; ++g) {
         const int slot = cidx % RING;  // even
         ok = mbar_wait_warp(&sh.r_full[slot], (cidx / RING) & 1, dead, p.err, 25) &&
@@ -428,7 +437,7 @@ __device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared
         for (int k = 0; k < 8; ++k) {
           const uint64_t bdesc = umma_desc(mndesc_hi, r_addr + slot * kWBlk + k * 2048);
           if (ROLE == ROLE_V)
-            umma_ts_w(tmem + Cfg::TMEM_ACC + g * 128, tmem + k * 8, bdesc, idesc_acc, t > 0 || k > 0);
+            umma_ts_w(tmem + Cfg::TMEM_ACC + g * 128, tmem + (t & 1) * 128 + k * 8, bdesc, idesc_acc, t > 0 || k > 0);
           else
             umma_ss_w(tmem + Cfg::TMEM_ACC + g * 128, umma_desc(kdesc_hi, ds_addr + (k / 4) * kWBlk + (k % 4) * 32), bdesc,
                       idesc_acc, t > 0 || k > 0);
@@ -437,8 +446,30 @@ __device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared
         umma_commit_w(&sh.r_empty[slot + 1]);
         cidx += 2;
       }
-      // S'(t+1) is issued behind these MMAs (in-order tensor pipe) and sdp_full(t+1) commits after them: the math warps
-      // cannot overwrite P' / dS' of tile t before its consumers have finished.
+      if (ok && HAS_DP) umma_commit_w(&sh.acc_done);  // the dS' tile may be rewritten
+    };
+    if (ok) issue_s(0);
+    for (int t = 0; t < T && ok; ++t) {
+      if (HAS_DP) {
+        // dP'(t): its TMEM columns were released by pass 2 of tile t-1 (pds_ready(t-1), waited below)
+        issue_dp();
+        if (!ok) break;
+        if (t + 1 < T) {  // S'(t+1) once pass 1 of tile t holds P' in registers
+          ok = mbar_wait_warp(&sh.s_consumed, t & 1, dead, p.err, 27);
+          if (!ok) break;
+          tc_fence_after();
+          issue_s(0);
+          if (!ok) break;
+        }
+      } else if (t + 1 < T) {
+        // S'(t+1) into the other buffer: its previous content P'(t-1) is read by acc(t-1), issued before (in-order pipe)
+        issue_s((t + 1) & 1);
+        if (!ok) break;
+      }
+      ok = mbar_wait_warp(&sh.pds_ready, t & 1, dead, p.err, 24);
+      if (!ok) break;
+      tc_fence_after();
+      issue_acc(t);
     }
     if (ok) umma_commit_w(&sh.acc_full);
   } else {
@@ -465,62 +496,91 @@ __device__ __forceinline__ void wide_bwd_body(unsigned char* smem, WideBwdShared
         pre_lse2 = load_lse2(t + 1);
         pre_dl = load_dl(t + 1);
       }
-      ok = mbar_wait_warp(&sh.sdp_full, t & 1, dead, p.err, 30);
+      const int buf = HAS_DP ? 0 : (t & 1);
+      ok = mbar_wait_warp(&sh.s_full[buf], (HAS_DP ? t : (t >> 1)) & 1, dead, p.err, 30);
       if (!ok) break;
       tc_fence_after();
       const int valid = n - t * 128;  // streamed rows (columns of S') that exist
-#pragma unroll 1
+      // ---- pass 1: P' = exp2(S' scale log2e - lse), packed fp16 ----
+      uint32_t pk[64];
+#pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t s[32], dp[32];
-        tmem_ld32(lane_addr + c0, s);
-        if (HAS_DP) tmem_ld32(lane_addr + Cfg::TMEM_DP + c0, dp);
+        uint32_t s[32];
+        tmem_ld32(lane_addr + buf * 128 + c0, s);
         tmem_ld_wait();
-        uint32_t pk[16], dk[16];
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
-          float nlv[4], ndv[4];
+          float nlv[4];
           if (COLSTAT) {
             const float4 nl = *reinterpret_cast<const float4*>(&sh.lse2[c0 + q]);
             nlv[0] = nl.x; nlv[1] = nl.y; nlv[2] = nl.z; nlv[3] = nl.w;
-            if (HAS_DP) {
-              const float4 nd = *reinterpret_cast<const float4*>(&sh.dl[c0 + q]);
-              ndv[0] = nd.x; ndv[1] = nd.y; ndv[2] = nd.z; ndv[3] = nd.w;
-            }
           } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { nlv[e] = my_lse2; ndv[e] = my_dl; }
+            for (int e = 0; e < 4; ++e) nlv[e] = my_lse2;
           }
-          float pv[4], dv[4];
+          float pv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             pv[e] = fast_exp2(fmaf(__uint_as_float(s[q + e]), p.scale_log2, nlv[e]));
-            dv[e] = HAS_DP ? pv[e] * fmaf(__uint_as_float(dp[q + e]), p.scale, ndv[e]) : 0.f;  // scale * P' * (dP' - delta)
-            if (!COLSTAT && c0 + q + e >= valid) { pv[e] = 0.f; dv[e] = 0.f; }  // keys past the end of the sequence
+            if (!COLSTAT && c0 + q + e >= valid) pv[e] = 0.f;  // keys past the end of the sequence
+            if (COLSTAT && !row_ok) pv[e] = 0.f;               // key rows past the end of the sequence
           }
-          pk[q >> 1] = pack_half2(pv[0], pv[1]);
-          pk[(q >> 1) + 1] = pack_half2(pv[2], pv[3]);
-          dk[q >> 1] = pack_half2(dv[0], dv[1]);
-          dk[(q >> 1) + 1] = pack_half2(dv[2], dv[3]);
+          pk[(c0 + q) >> 1] = pack_half2(pv[0], pv[1]);
+          pk[((c0 + q) >> 1) + 1] = pack_half2(pv[2], pv[3]);
         }
-        if (COLSTAT && !row_ok) {  // key rows past the end of the sequence
-#pragma unroll
-          for (int e = 0; e < 16; ++e) { pk[e] = 0u; dk[e] = 0u; }
-        }
-        if (ROLE == ROLE_V) {
-          // P' (packed fp16) over the S' columns this thread has already read: columns [c0/2, c0/2 + 16)
-          tmem_st16(lane_addr + (c0 >> 1), pk);
-        } else {
-          // dS' row r, streamed columns [c0, c0 + 32): four 16-byte chunks of block c0 / 64
-          unsigned char* ds_blk = sDS + (c0 >> 6) * kWBlk;
-          const int chunk0 = (c0 & 63) >> 3;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            *reinterpret_cast<uint4*>(ds_blk + sw128_offset(r, chunk0 + cc)) =
-                make_uint4(dk[4 * cc], dk[4 * cc + 1], dk[4 * cc + 2], dk[4 * cc + 3]);
-        }
+        // role V: P' over the S' columns this thread has already read: columns [c0/2, c0/2 + 16) of its buffer
+        if (ROLE == ROLE_V) tmem_st16(lane_addr + buf * 128 + (c0 >> 1), pk + (c0 >> 1));
       }
-      if (ROLE == ROLE_V) tmem_st_wait();
-      else fence_proxy_async_smem();
+      if (ROLE == ROLE_V) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.pds_ready);
+        continue;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh.s_consumed);  // S'(t) is in registers: S'(t+1) may be issued
+      // ---- pass 2: dS' = scale P' (dP' - delta) -> smem ----
+      ok = mbar_wait_warp(&sh.dp_full, t & 1, dead, p.err, 32);
+      if (ok && t > 0) ok = mbar_wait_warp(&sh.acc_done, (t - 1) & 1, dead, p.err, 33);  // acc(t-1) has read the dS' tile
+      if (!ok) break;
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t dp[32];
+        tmem_ld32(lane_addr + Cfg::TMEM_DP + c0, dp);
+        tmem_ld_wait();
+        uint32_t dk[16];
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          float ndv[4];
+          if (COLSTAT) {
+            const float4 nd = *reinterpret_cast<const float4*>(&sh.dl[c0 + q]);
+            ndv[0] = nd.x; ndv[1] = nd.y; ndv[2] = nd.z; ndv[3] = nd.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ndv[e] = my_dl;
+          }
+          const float2 p01 = __half22float2(*reinterpret_cast<const __half2*>(&pk[(c0 + q) >> 1]));
+          const float2 p23 = __half22float2(*reinterpret_cast<const __half2*>(&pk[((c0 + q) >> 1) + 1]));
+          // scale * P' * (dP' - delta); masked rows / columns have P' = 0
+          const float d0 = p01.x * fmaf(__uint_as_float(dp[q]), p.scale, ndv[0]);
+          const float d1 = p01.y * fmaf(__uint_as_float(dp[q + 1]), p.scale, ndv[1]);
+          const float d2 = p23.x * fmaf(__uint_as_float(dp[q + 2]), p.scale, ndv[2]);
+          const float d3 = p23.y * fmaf(__uint_as_float(dp[q + 3]), p.scale, ndv[3]);
+          dk[q >> 1] = pack_half2(d0, d1);
+          dk[(q >> 1) + 1] = pack_half2(d2, d3);
+        }
+        // dS' row r, streamed columns [c0, c0 + 32): four 16-byte chunks of block c0 / 64
+        unsigned char* ds_blk = sDS + (c0 >> 6) * kWBlk;
+        const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          *reinterpret_cast<uint4*>(ds_blk + sw128_offset(r, chunk0 + cc)) =
+              make_uint4(dk[4 * cc], dk[4 * cc + 1], dk[4 * cc + 2], dk[4 * cc + 3]);
+      }
+      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.pds_ready);
@@ -567,8 +627,12 @@ sattn_wide_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
     sh.dead = 0;
     mbar_init(&sh.x_full, 1);
     for (int i = 0; i < Cfg::RING_V; ++i) { mbar_init(&sh.r_full[i], 1); mbar_init(&sh.r_empty[i], 1); }
-    mbar_init(&sh.sdp_full, 1);
+    mbar_init(&sh.s_full[0], 1);
+    mbar_init(&sh.s_full[1], 1);
+    mbar_init(&sh.s_consumed, 4);
+    mbar_init(&sh.dp_full, 1);
     mbar_init(&sh.pds_ready, 4);
+    mbar_init(&sh.acc_done, 1);
     mbar_init(&sh.acc_full, 1);
     mbar_fence_init();
   }

@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from diffusion_spacetime_attn_b200 import native, ops  # noqa: E402
 
-which = sys.argv[1:] or ["sattn", "xattn", "tokens"]
+which = sys.argv[1:] or ["sattn", "wide", "xattn", "tokens"]
 g = torch.Generator(device="cuda").manual_seed(0)
 rnd = lambda *s: torch.randn(*s, device="cuda", generator=g).half()
 if "sattn" in which:
@@ -18,6 +18,13 @@ if "sattn" in which:
         ops.sattn_bwd(q, k, v, out, lse, do, h)
         torch.cuda.synchronize()
         print("sattn", (b, n, h, d), "ok", float(out.float().abs().mean()))
+if "wide" in which:  # 512-wide head (VAE AttnBlock): two key tiles, ragged, so every ring / pipeline barrier wraps at least once
+    for (b, n) in [(1, 200)]:
+        q, k, v, do = rnd(b, n, 512), rnd(b, n, 512), rnd(b, n, 512), rnd(b, n, 512) * 0.1
+        out, lse = ops.sattn_fwd(q, k, v, 1)
+        ops.sattn_bwd(q, k, v, out, lse, do, 1)
+        torch.cuda.synchronize()
+        print("wide", (b, n, 1, 512), "ok", float(out.float().abs().mean()))
 if "xattn" in which:
     for (B, n, h, d, n_obj) in [(1, 144, 2, 40, 3), (1, 100, 1, 80, 2), (2, 64, 1, 160, 2)]:
         C = h * d
