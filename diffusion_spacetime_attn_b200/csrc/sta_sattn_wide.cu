@@ -31,8 +31,12 @@ constexpr int kWNB = kWD / 64;           // blocks per full-width tile
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
+// DV = output columns per CTA.  256 (two slices, the scores computed twice) is the efficient shape once the grid fills the
+// GPU; one 64 x 64 latent gives only 64 such CTAs, so the launcher picks DV = 128 (128 CTAs, scores computed four times
+// but on otherwise idle SMs) whenever the 256-column grid would leave SMs empty.
+template <int DV_>
 struct WideFwdCfg {
-  static constexpr int DV = 256;              // output columns per CTA
+  static constexpr int DV = DV_;
   static constexpr int NSL = kWD / DV;        // column slices
   static constexpr int NVB = DV / 64;         // V blocks per key tile
   static constexpr int RING = 6;              // even: a pair of adjacent blocks (N = 128 operand) never wraps
@@ -50,10 +54,11 @@ struct WideFwdParams {
   unsigned int* err;
 };
 
-__global__ void __launch_bounds__(WideFwdCfg::THREADS, 1)
+template <int DV_>
+__global__ void __launch_bounds__(WideFwdCfg<DV_>::THREADS, 1)
 sattn_wide_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                       const __grid_constant__ CUtensorMap tm_v, const WideFwdParams p) {
-  using Cfg = WideFwdCfg;
+  using Cfg = WideFwdCfg<DV_>;
   constexpr int RING = Cfg::RING, DV = Cfg::DV;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -704,8 +709,23 @@ static int wide_tmap(CUtensorMap* m, const void* ptr, int heads, int n, int batc
   return make_tmap_f16(m, ptr, 4, dims, st, box);
 }
 
+template <int DV>
+static int launch_wide_fwd_dv(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v, const WideFwdParams& p,
+                              const sta_sattn_fwd_args* a, cudaStream_t stream) {
+  using Cfg = WideFwdCfg<DV>;
+  static PerDeviceOnce smem_attr;
+  int rc;
+  if ((rc = smem_attr.run([] {
+        return cudaFuncSetAttribute(sattn_wide_fwd_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+      })))
+    return rc;
+  dim3 grid((a->n + 127) / 128, a->heads * Cfg::NSL, a->batch);
+  sattn_wide_fwd_kernel<DV><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tm_q, tm_k, tm_v, p);
+  STA_CUDA_CHECK(cudaGetLastError());
+  return STA_OK;
+}
+
 int launch_sattn_wide_fwd(const sta_sattn_fwd_args* a, cudaStream_t stream) {
-  using Cfg = WideFwdCfg;
   CUtensorMap tm_q, tm_k, tm_v;
   int rc;
   if ((rc = wide_tmap(&tm_q, a->q, a->heads, a->n, a->batch, a->q_token_stride, a->q_batch_stride))) return rc;
@@ -720,15 +740,17 @@ int launch_sattn_wide_fwd(const sta_sattn_fwd_args* a, cudaStream_t stream) {
   p.o_batch_stride = a->o_batch_stride;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.err = device_error_word();
-  static PerDeviceOnce smem_attr;
-  if ((rc = smem_attr.run([] {
-        return cudaFuncSetAttribute(sattn_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-      })))
-    return rc;
-  dim3 grid((a->n + 127) / 128, a->heads * Cfg::NSL, a->batch);
-  sattn_wide_fwd_kernel<<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(tm_q, tm_k, tm_v, p);
-  STA_CUDA_CHECK(cudaGetLastError());
-  return STA_OK;
+  static std::atomic<int> sm_count{0};  // every GPU of a box has the same SM count: one query per process
+  int num_sms = sm_count.load(std::memory_order_relaxed);
+  if (num_sms == 0) {
+    int dev = 0;
+    num_sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    sm_count.store(num_sms, std::memory_order_relaxed);
+  }
+  const long long ctas256 = (long long)((a->n + 127) / 128) * a->heads * 2 * a->batch;
+  if (ctas256 < num_sms) return launch_wide_fwd_dv<128>(tm_q, tm_k, tm_v, p, a, stream);
+  return launch_wide_fwd_dv<256>(tm_q, tm_k, tm_v, p, a, stream);
 }
 
 int launch_sattn_wide_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {

@@ -13,8 +13,9 @@ import torch
 from diffusion_spacetime_attn_b200 import native, ops
 from oracle import sta_oracle as O
 
-# (batch, n, heads): one tile, two tiles, ragged, two heads / two prompts, the 512^2 decode (64 x 64 latent), ragged large
-SHAPES = [(1, 128, 1), (1, 256, 1), (2, 300, 1), (2, 640, 2), (1, 4096, 1), (1, 1100, 1)]
+# (batch, n, heads): one tile, two tiles, ragged, two heads / two prompts, the 512^2 decode (64 x 64 latent), ragged large,
+# and a grid of 160 CTAs (>= the SM count: the 256-column variant of the forward; the others run the 128-column one)
+SHAPES = [(1, 128, 1), (1, 256, 1), (2, 300, 1), (2, 640, 2), (1, 4096, 1), (1, 1100, 1), (4, 1280, 2)]
 D = 512
 
 
