@@ -50,8 +50,10 @@ int sta_device_error(unsigned int* code_out, int clear);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Self-attention (attn1).  Tokens are laid out [batch, n, heads * head_dim] fp16 with arbitrary token/batch
- * strides (in ELEMENTS) so q/k/v may be slices of one fused projection.  head_dim in {40, 80, 160} (SD-v1) or
- * any multiple of 8 up to 160; strides and base pointers must keep every row 16-byte aligned.
+ * strides (in ELEMENTS) so q/k/v may be slices of one fused projection.  head_dim in {40, 80, 160} (SD-v1 UNet) or 512:
+ * the single-head mid-block AttnBlock of SD-v1's KL-VAE decoder, ldm/modules/diffusionmodules/model.py:150-202 (a
+ * K-dim-pipelined kernel of its own, csrc/sta_sattn_wide.cu; its backward needs no dq_accum, which may be NULL).  Any
+ * other head_dim is STA_ERR_UNSUPPORTED; strides and base pointers must keep every row 16-byte aligned.
  * lse (optional, may be NULL): fp32 [batch, heads, n], natural-log-sum-exp of the scaled scores.
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct {
