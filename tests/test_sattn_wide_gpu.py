@@ -15,7 +15,7 @@ from oracle import sta_oracle as O
 
 # (batch, n, heads): one tile, two tiles, ragged, two heads / two prompts, the 512^2 decode (64 x 64 latent), ragged large,
 # and a grid of 160 CTAs (>= the SM count: the 256-column variant of the forward; the others run the 128-column one)
-SHAPES = [(1, 128, 1), (1, 256, 1), (2, 300, 1), (2, 640, 2), (1, 4096, 1), (1, 1100, 1), (4, 1280, 2)]
+SHAPES = [(1, 128, 1), (1, 256, 1), (2, 300, 1), (2, 640, 2), (1, 4096, 1), (1, 1100, 1), (4, 1280, 2), (1, 77, 1), (1, 8, 1)]
 D = 512
 
 
@@ -64,7 +64,7 @@ def test_wide_fwd_large_logits_rescale_path_and_strided_views():
     _close(out, ref, atol=4e-3, rtol=2e-2)
 
 
-BWD_SHAPES = [(1, 128, 1), (1, 384, 1), (2, 300, 1), (1, 640, 2), (1, 4096, 1)]
+BWD_SHAPES = [(1, 128, 1), (1, 384, 1), (2, 300, 1), (1, 640, 2), (1, 4096, 1), (1, 77, 1), (1, 8, 1)]
 
 
 @pytest.mark.gpu

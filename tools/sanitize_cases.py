@@ -25,6 +25,10 @@ if "wide" in which:  # 512-wide head (VAE AttnBlock): two key tiles, ragged, so 
         ops.sattn_bwd(q, k, v, out, lse, do, 1)
         torch.cuda.synchronize()
         print("wide", (b, n, 1, 512), "ok", float(out.float().abs().mean()))
+    q, k, v = rnd(10, 1000, 512), rnd(10, 1000, 512), rnd(10, 1000, 512)  # 160 CTAs: the forward's 256-column variant
+    out, _ = ops.sattn_fwd(q, k, v, 1)
+    torch.cuda.synchronize()
+    print("wide fwd256", (10, 1000, 1, 512), "ok", float(out.float().abs().mean()))
 if "xattn" in which:
     for (B, n, h, d, n_obj) in [(1, 144, 2, 40, 3), (1, 100, 1, 80, 2), (2, 64, 1, 160, 2)]:
         C = h * d
