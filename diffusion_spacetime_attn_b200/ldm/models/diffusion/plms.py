@@ -275,9 +275,10 @@ class PLMSSampler(object):
                         loss.backward()
                     alpha_grads.append(W.grad.detach().clone())  # dL/dalpha of this epoch (diagnostics / parity tests)
                     optimizer.step()
-                    losses.append([float(v) for v in torch.stack(per_prompt).detach().cpu()])
+                    losses.append(torch.stack(per_prompt).detach())  # read back after the last epoch: no host sync per epoch
             if epoch == epochs - 1 and self.save_images and decoded is not None:
                 self._save(decoded.detach(), epoch if do_opt else 2, seed, idxs)
+        losses = [[float(v) for v in t.cpu()] for t in losses]
         if runner is not None:
             runner.active = None
         unet.set_local_contexts(None)

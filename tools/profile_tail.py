@@ -17,6 +17,7 @@ from diffusion_spacetime_attn_b200.pipeline import SpaceTimeAttnPipeline  # noqa
 
 pipe = SpaceTimeAttnPipeline(steps=50, num_epochs=3, save_images=False)
 items = [it for it in P.build_work_items(P.read_gpt(P.SYNTHETIC_GPT)) if len(it.object_names) == 2][:4]
+items = (items * 3)[:8]
 conds = [pipe.to_device(pipe.encode([it])) for it in items]
 pipe.generate([items[0]], conds[0])
 torch.cuda.synchronize()
@@ -30,12 +31,14 @@ def timed(i):
     return time.perf_counter() - t0
 
 
-full = timed(1)
+# medians of three images each way (a single pair of images differs by +-1 % = +-5 ms per epoch on its own)
+full = sorted(timed(i) for i in (1, 2, 3))[1]
 s = pipe.sampler
 real_decode, real_loss = s.decode_fn, s.loss_fn
 s.decode_fn = lambda z: z
 s.loss_fn = lambda imgs, *a: (imgs.float().sum(), [imgs.float().sum()])
-bare = timed(2)
+timed(4)
+bare = sorted(timed(i) for i in (5, 6, 7))[1]
 s.decode_fn, s.loss_fn = real_decode, real_loss
 print(f"image with VAE+CLIP tail: {full * 1e3:.0f} ms; trajectory only: {bare * 1e3:.0f} ms; tail = {(full - bare) * 1e3 / 3:.1f} ms per epoch")
 
