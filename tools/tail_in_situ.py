@@ -50,6 +50,16 @@ def loss(*a):
 
 
 s.decode_fn, s.loss_fn = decode, loss
+traj_start = []
+real_traj = s._trajectory
+
+
+def traj(*a, **k):
+    traj_start.append(ev())  # also marks the end of the previous epoch's backward + Adam step
+    return real_traj(*a, **k)
+
+
+s._trajectory = traj
 # host time per piece of the loss call (where does the host block?)
 clip = s.clip_loss_model
 host = {}
@@ -80,5 +90,14 @@ for k, r in enumerate(rec):
     print(f"epoch {k}: GPU decode fwd {r['a'].elapsed_time(r['b']):6.2f} ms, loss fwd {r['b'].elapsed_time(r['c']):6.2f} ms, "
           f"tail backward {r['c'].elapsed_time(r['d']):6.2f} ms, total {r['a'].elapsed_time(r['d']):6.2f} ms | host: decode call "
           f"{1e3 * (r['h1'] - r['h0']):6.2f} ms, loss call {1e3 * (r['h2'] - r['h1']):6.2f} ms")
+traj_start.append(ev())
+torch.cuda.synchronize()
+for k, r in enumerate(rec):
+    fwd = traj_start[k].elapsed_time(r["a"])
+    line = f"epoch {k}: forward trajectory {fwd:7.2f} ms = 51 x {fwd / 51:.3f}"
+    if k % 3 != 2:  # the next trajectory of the same image starts right behind this epoch's backward
+        bwd = r["d"].elapsed_time(traj_start[k + 1])
+        line += f"; trajectory backward + Adam {bwd:7.2f} ms = 50 x {bwd / 50:.3f}"
+    print(line)
 for nm, v in host.items():
     print(f"host {nm}: " + " ".join(f"{x:.2f}" for x in v[:24]))
