@@ -385,6 +385,19 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 // byte offset of element (row r, 16-byte chunk c) inside one SW128 block
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 
+// n / d for n < 2^31 by the divisor's magic number (host side: make_fast_div in sta_host.h): q = (umulhi(n, magic) + n) >> shift.
+// A 64-bit `i / runtime_value` is ~100 SASS instructions of emulated division — it made the elementwise kernels issue-bound.
+struct FastDiv {
+  unsigned int d, magic, shift;
+};
+__device__ __forceinline__ unsigned int fast_div(unsigned int n, const FastDiv& f) {
+  return (__umulhi(n, f.magic) + n) >> f.shift;
+}
+__device__ __forceinline__ void fast_divmod(unsigned int n, const FastDiv& f, unsigned int& q, unsigned int& r) {
+  q = fast_div(n, f);
+  r = n - q * f.d;
+}
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -60,6 +60,15 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 int make_tmap_f32_dense(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box, int swizzle_bytes = 0);  // 0 (dense rows), 32 or 64: smem-side XOR swizzle
 
+// magic number of sta_common.cuh's fast_div for the divisor d >= 1 (valid for dividends < 2^31)
+struct FastDiv;
+inline void make_fast_div_raw(unsigned int d, unsigned int* magic, unsigned int* shift) {
+  unsigned int sh = 0;
+  while ((1ull << sh) < d) ++sh;
+  *shift = sh;
+  *magic = (unsigned int)((((1ull << 32) * ((1ull << sh) - d)) / d + 1) & 0xffffffffull);
+}
+
 // head dim 512 (KL-VAE mid-block AttnBlock): sta_sattn_wide.cu, reached through sta_sattn_fwd / sta_sattn_bwd
 int launch_sattn_wide_fwd(const sta_sattn_fwd_args* a, cudaStream_t stream);
 int launch_sattn_wide_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream);

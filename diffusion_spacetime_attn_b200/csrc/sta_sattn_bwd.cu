@@ -488,19 +488,20 @@ sattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // first version used one thread per (b, i, h) with D/4 dependent-address loads: 6.9 us for the 4096 (b, i, h) of N = 256.
 template <int D>
 __global__ void __launch_bounds__(256) sattn_delta_kernel(const __half* __restrict__ o, const __half* __restrict__ d_o,
-                                                          float* __restrict__ delta, float* __restrict__ dq_accum, int batch,
-                                                          int n, int heads, long long o_ts, long long o_bs, long long do_ts,
+                                                          float* __restrict__ delta, float* __restrict__ dq_accum, int n,
+                                                          int heads, long long o_ts, long long o_bs, long long do_ts,
                                                           long long do_bs) {
   constexpr int L = D <= 64 ? 8 : (D <= 128 ? 16 : 32);
   constexpr int VEC = D / 8;
-  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  // grid.y = batch sample, 32-bit index math inside it: the first version decomposed a 64-bit flat index with four emulated
+  // 64-bit divisions (197 of its 312 SASS instructions) and was issue-bound (5.8 us for the 64 x 64 level)
+  const unsigned int item = (blockIdx.x * blockDim.x + threadIdx.x) / L;  // (token, head) of this sample
   const int sub = threadIdx.x & (L - 1);
-  const long long total = (long long)batch * n * heads;
-  const bool live = item < total;  // dead items still take part in the shuffles
-  const long long it = live ? item : total - 1;
-  const int h = it % heads;
-  const long long bi = it / heads;
-  const int i = bi % n, b = bi / n;
+  const unsigned int per_sample = (unsigned int)n * (unsigned int)heads;
+  const bool live = item < per_sample;  // dead items still take part in the shuffles
+  const unsigned int it = live ? item : per_sample - 1;
+  const unsigned int i = it / (unsigned int)heads, h = it - i * (unsigned int)heads;
+  const long long b = blockIdx.y;
   float acc = 0.f;
   if (sub < VEC) {
     const uint4 a = *reinterpret_cast<const uint4*>(o + b * o_bs + i * o_ts + h * D + sub * 8);
@@ -514,27 +515,28 @@ __global__ void __launch_bounds__(256) sattn_delta_kernel(const __half* __restri
       acc = fmaf(x.y, y.y, acc);
     }
     if (live) {  // the lane's 8 columns of the fp32 dQ accumulator
-      float4* z = reinterpret_cast<float4*>(dq_accum + ((bi * heads + h) * D) + sub * 8);
+      float4* z = reinterpret_cast<float4*>(dq_accum + (((b * n + i) * heads + h) * D) + sub * 8);
       z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
       z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 #pragma unroll
   for (int off = L >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (live && sub == 0) delta[((long long)b * heads + h) * n + i] = acc;
+  if (live && sub == 0) delta[(b * heads + h) * n + i] = acc;
 }
 
 // dq_accum fp32 [rows, c] dense -> d_q fp16 [rows, c] with row stride d_tok (d_q may be a slice of one d(qkv) buffer)
-__global__ void sattn_dq_cast_kernel(const float4* __restrict__ src, __half* __restrict__ dst, long long n4, int c4,
+__global__ void sattn_dq_cast_kernel(const float4* __restrict__ src, __half* __restrict__ dst, unsigned int n4, FastDiv c4,
                                      long long d_tok) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;  // n4 < 2^31 (checked by the launcher)
   if (idx >= n4) return;
   const float4 v = src[idx];
   uint2 o;
   o.x = pack_half2(v.x, v.y);
   o.y = pack_half2(v.z, v.w);
-  const long long row = idx / c4;
-  *reinterpret_cast<uint2*>(dst + row * d_tok + (idx - row * c4) * 4) = o;
+  unsigned int row, col4;
+  fast_divmod(idx, c4, row, col4);  // (a 64-bit idx / c4 was 111 of this kernel's 168 SASS instructions)
+  *reinterpret_cast<uint2*>(dst + (long long)row * d_tok + col4 * 4) = o;
 }
 
 template <int D>
@@ -554,7 +556,6 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   if ((rc = mk(&tm_do, a->d_out, a->do_token_stride, a->do_batch_stride))) return rc;
 
   const long long C = (long long)a->heads * D;
-  const long long total = (long long)a->batch * a->n * a->heads;
   CUtensorMap tm_dq, tm_dq1;
   {
     const uint64_t st[4] = {4, (uint64_t)D * 4, (uint64_t)C * 4, (uint64_t)a->n * C * 4};
@@ -566,9 +567,13 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   }
   {  // delta and the zeroing of dq_accum in one launch
     constexpr int L = D <= 64 ? 8 : (D <= 128 ? 16 : 32);
-    sattn_delta_kernel<D><<<(unsigned)((total * L + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<const __half*>(a->out), reinterpret_cast<const __half*>(a->d_out), a->delta, a->dq_accum, a->batch,
-        a->n, a->heads, a->o_token_stride, a->o_batch_stride, a->do_token_stride, a->do_batch_stride);
+    const long long per_sample = (long long)a->n * a->heads;
+    if (per_sample * L >= (1ll << 31) || a->batch > 65535)
+      return fail(STA_ERR_UNSUPPORTED, "sta_sattn_bwd: n * heads = %lld / batch %d exceed the 32-bit index range", per_sample, a->batch);
+    const dim3 dgrid((unsigned)((per_sample * L + 255) / 256), (unsigned)a->batch);
+    sattn_delta_kernel<D><<<dgrid, 256, 0, stream>>>(
+        reinterpret_cast<const __half*>(a->out), reinterpret_cast<const __half*>(a->d_out), a->delta, a->dq_accum, a->n,
+        a->heads, a->o_token_stride, a->o_batch_stride, a->do_token_stride, a->do_batch_stride);
   }
   STA_CUDA_CHECK(cudaGetLastError());
 
@@ -599,8 +604,12 @@ static int launch_sattn_bwd(const sta_sattn_bwd_args* a, cudaStream_t stream) {
   STA_CUDA_CHECK(cudaGetLastError());
 
   const long long n4 = (long long)a->batch * a->n * C / 4;
+  if (n4 >= (1ll << 31)) return fail(STA_ERR_UNSUPPORTED, "sta_sattn_bwd: %lld gradient vectors exceed the 32-bit index range", n4);
+  FastDiv c4;
+  c4.d = (unsigned int)(C / 4);
+  make_fast_div_raw(c4.d, &c4.magic, &c4.shift);
   sattn_dq_cast_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const float4*>(a->dq_accum), reinterpret_cast<__half*>(a->d_q), n4, (int)(C / 4), p.d_tok);
+      reinterpret_cast<const float4*>(a->dq_accum), reinterpret_cast<__half*>(a->d_q), (unsigned int)n4, c4, p.d_tok);
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
 }

@@ -298,14 +298,10 @@ struct GegluParams {
   __half* out;         // fwd [rows, inner]; bwd [rows, 2*inner]
   long long vec_total; // rows * inner / 8   (< 2^31, checked by the launcher)
   int inner_vecs;      // inner / 8
-  unsigned int div_magic, div_shift;  // row = vector index / inner_vecs without an integer division (fast_div below)
+  FastDiv div_inner;   // row = vector index / inner_vecs without an integer division (sta_common.cuh).  The first version
+                       // divided a 64-bit index by inner_vecs per vector: ~120 of the 440 SASS instructions of the loop body.
 };
 
-// n / d for n < 2^31 with the divisor's magic number (host: geglu_divisor): q = (umulhi(n, magic) + n) >> shift.  The first
-// version divided a 64-bit index by inner_vecs per vector: ~120 of the 440 SASS instructions of the loop body.
-__device__ __forceinline__ unsigned int fast_div(unsigned int n, unsigned int magic, unsigned int shift) {
-  return (__umulhi(n, magic) + n) >> shift;
-}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -337,7 +333,7 @@ __device__ __forceinline__ float gelu_cdf(float x) {
 __global__ void __launch_bounds__(256) geglu_fwd_kernel(GegluParams p) {
   const unsigned int total = (unsigned int)p.vec_total, step = gridDim.x * blockDim.x, iv = (unsigned int)p.inner_vecs;
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const unsigned int row = fast_div(i, p.div_magic, p.div_shift);
+    const unsigned int row = fast_div(i, p.div_inner);
     const __half* pr = p.proj + ((size_t)row * iv + i) * 8;  // (row * 2 iv + (i - row * iv)) * 8
     float a[8], g[8];
     tk_unpack8(*reinterpret_cast<const uint4*>(pr), a);
@@ -351,7 +347,7 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(GegluParams p) {
 __global__ void __launch_bounds__(256) geglu_bwd_kernel(GegluParams p) {
   const unsigned int total = (unsigned int)p.vec_total, step = gridDim.x * blockDim.x, iv = (unsigned int)p.inner_vecs;
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
-    const unsigned int row = fast_div(i, p.div_magic, p.div_shift);
+    const unsigned int row = fast_div(i, p.div_inner);
     const size_t off = ((size_t)row * iv + i) * 8;  // (row * 2 iv + (i - row * iv)) * 8
     float a[8], g[8], d[8], da[8], dg[8];
     tk_unpack8(*reinterpret_cast<const uint4*>(p.proj + off), a);
@@ -376,33 +372,32 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(GegluParams p) {
 struct Up2Params {
   const __half* src;
   __half* dst;
-  long long vec_total;  // vectors of the tensor the thread index runs over (forward: output, backward: input gradient)
+  long long vec_total;  // vectors of the tensor the thread index runs over (forward: output, backward: input gradient); < 2^31
   int h, w, cvecs;      // INPUT height / width, channel vectors
+  FastDiv div_c, div_x, div_y;  // channel vectors, then the x and y extents of the tensor the index runs over
 };
 
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(Up2Params p) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.vec_total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % p.cvecs);
-    long long t = i / p.cvecs;
-    const int ox = (int)(t % (2 * p.w));
-    t /= 2 * p.w;
-    const int oy = (int)(t % (2 * p.h));
-    const long long b = t / (2 * p.h);
-    const long long in = ((b * p.h + (oy >> 1)) * p.w + (ox >> 1)) * p.cvecs + cv;
+  const unsigned int total = (unsigned int)p.vec_total, step = gridDim.x * blockDim.x;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    unsigned int t, cv, ox, oy, b;
+    fast_divmod(i, p.div_c, t, cv);   // div_x = 2 w, div_y = 2 h (output extents)
+    fast_divmod(t, p.div_x, t, ox);
+    fast_divmod(t, p.div_y, b, oy);
+    const size_t in = (((size_t)b * p.h + (oy >> 1)) * p.w + (ox >> 1)) * p.cvecs + cv;
     reinterpret_cast<uint4*>(p.dst)[i] = reinterpret_cast<const uint4*>(p.src)[in];
   }
 }
 
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(Up2Params p) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.vec_total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % p.cvecs);
-    long long t = i / p.cvecs;
-    const int x = (int)(t % p.w);
-    t /= p.w;
-    const int y = (int)(t % p.h);
-    const long long b = t / p.h;
-    const long long row = (long long)2 * p.w * p.cvecs;
-    const long long o = ((b * 2 * p.h + 2 * y) * 2 * p.w + 2 * x) * p.cvecs + cv;
+  const unsigned int total = (unsigned int)p.vec_total, step = gridDim.x * blockDim.x;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    unsigned int t, cv, x, y, b;
+    fast_divmod(i, p.div_c, t, cv);   // div_x = w, div_y = h (input extents)
+    fast_divmod(t, p.div_x, t, x);
+    fast_divmod(t, p.div_y, b, y);
+    const size_t row = (size_t)2 * p.w * p.cvecs;
+    const size_t o = (((size_t)b * 2 * p.h + 2 * y) * 2 * p.w + 2 * x) * p.cvecs + cv;
     const uint4* g = reinterpret_cast<const uint4*>(p.src);
     float a[8], c[8], acc[8];
     tk_unpack8(g[o], acc);
@@ -488,13 +483,13 @@ extern "C" int sta_add_layernorm_bwd(const sta_add_layernorm_bwd_args* a, void* 
   return STA_OK;
 }
 
-static void geglu_divisor(sta::GegluParams* p) {  // magic number of fast_div for d = inner_vecs
-  const unsigned int d = (unsigned int)p->inner_vecs;
-  unsigned int sh = 0;
-  while ((1ull << sh) < d) ++sh;
-  p->div_shift = sh;
-  p->div_magic = (unsigned int)((((1ull << 32) * ((1ull << sh) - d)) / d + 1) & 0xffffffffull);
+static sta::FastDiv host_fast_div(unsigned int d) {
+  sta::FastDiv f;
+  f.d = d;
+  sta::make_fast_div_raw(d, &f.magic, &f.shift);
+  return f;
 }
+static void geglu_divisor(sta::GegluParams* p) { p->div_inner = host_fast_div((unsigned int)p->inner_vecs); }
 
 static int geglu_check(const sta_geglu_args* a, bool bwd, const char* who) {
   using namespace sta;
@@ -557,6 +552,8 @@ extern "C" int sta_upsample2x_fwd(const sta_upsample2x_args* a, void* stream) {
   p.dst = reinterpret_cast<__half*>(a->out);
   p.h = a->height; p.w = a->width; p.cvecs = a->channels / 8;
   p.vec_total = (long long)a->batch * 4 * a->height * a->width * p.cvecs;
+  if (p.vec_total >= (1ll << 31)) return fail(STA_ERR_UNSUPPORTED, "sta_upsample2x_fwd: more than 2^31 vectors (32-bit indexing)");
+  p.div_c = host_fast_div(p.cvecs); p.div_x = host_fast_div(2 * a->width); p.div_y = host_fast_div(2 * a->height);
   upsample2x_fwd_kernel<<<geglu_grid(p.vec_total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
@@ -571,6 +568,8 @@ extern "C" int sta_upsample2x_bwd(const sta_upsample2x_args* a, void* stream) {
   p.dst = reinterpret_cast<__half*>(a->out);
   p.h = a->height; p.w = a->width; p.cvecs = a->channels / 8;
   p.vec_total = (long long)a->batch * a->height * a->width * p.cvecs;
+  if (p.vec_total >= (1ll << 31)) return fail(STA_ERR_UNSUPPORTED, "sta_upsample2x_bwd: more than 2^31 vectors (32-bit indexing)");
+  p.div_c = host_fast_div(p.cvecs); p.div_x = host_fast_div(a->width); p.div_y = host_fast_div(a->height);
   upsample2x_bwd_kernel<<<geglu_grid(p.vec_total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   STA_CUDA_CHECK(cudaGetLastError());
   return STA_OK;
