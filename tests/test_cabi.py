@@ -125,3 +125,48 @@ def test_ops_refuse_cpu_tensors():
     q = torch.zeros(1, 16, 320, dtype=torch.float16)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.sattn_fwd(q, q, q, heads=8)
+
+
+def test_fast_div_magic_numbers_divide_exactly(tmp_path):
+    """The elementwise kernels replace `index / runtime_divisor` by (umulhi(n, magic) + n) >> shift (csrc/sta_common.cuh
+    fast_div) with magic / shift from csrc/sta_host.h make_fast_div_raw: compile that host function with g++ and check the
+    quotient against the C division for the divisors the launchers pass (channel vectors, widths, heights) and awkward ones,
+    over small, random and the largest allowed (< 2^31) dividends."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    cuda_inc = Path("/usr/local/cuda/include")
+    if gxx is None or not (cuda_inc / "cuda_runtime.h").exists():
+        pytest.skip("g++ / CUDA headers not available")
+    src = tmp_path / "fastdiv.cpp"
+    src.write_text(f'''
+#include "{ROOT / "diffusion_spacetime_attn_b200" / "csrc" / "sta_host.h"}"
+#include <stdlib.h>
+int main() {{
+  const unsigned int divisors[] = {{1, 2, 3, 5, 7, 12, 40, 64, 80, 96, 125, 128, 160, 192, 256, 320, 640, 1000, 1280, 4095, 4096,
+                                   65537, (1u << 20) + 7, (1u << 30) + 1, (1u << 31) - 1}};
+  unsigned long long bad = 0, checked = 0;
+  srand(1);
+  for (unsigned int d : divisors) {{
+    unsigned int magic, shift;
+    sta::make_fast_div_raw(d, &magic, &shift);
+    auto check = [&](unsigned int n) {{
+      const unsigned int q = (unsigned int)((((unsigned long long)n * magic) >> 32) + n) >> shift;  // 32-bit add, as on the device
+      bad += q != n / d;
+      ++checked;
+    }};
+    for (unsigned int n = 0; n < 70000; ++n) check(n);
+    for (int i = 0; i < 200000; ++i) check((((unsigned int)rand() << 16) ^ (unsigned int)rand()) & 0x7fffffffu);
+    for (unsigned int n = 0x7fffffffu; n > 0x7fffffffu - 1000; --n) check(n);
+    for (unsigned int k = 1; k < 2000 && (unsigned long long)k * d < (1ull << 31); ++k) {{ check(k * d); check(k * d - 1); }}
+  }}
+  printf("%llu %llu\\n", bad, checked);
+  return bad != 0;
+}}
+''')
+    exe = tmp_path / "fastdiv"
+    subprocess.run([gxx, "-std=c++17", "-O1", f"-I{cuda_inc}", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    bad, checked = out.stdout.split()
+    assert out.returncode == 0 and int(bad) == 0 and int(checked) > 1_000_000, out.stdout
